@@ -1,0 +1,170 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the dev container.
+
+TEST INFRASTRUCTURE.  Run here only (needs /root/reference, which does not exist on the
+GPU box):   python oracle/gen_golden.py [--out tests/golden]
+
+For every case the reference's ``PlankModel`` (imported from /root/reference) is given
+seeded weights (``synthetic.init_state_dict`` or the committed trained checkpoint) and
+seeded synthetic batches (``synthetic.make_batch``); its train-mode outputs, gradients and
+greedy-decode outputs are recorded.  Tests re-create weights and inputs from the same seeds,
+so the fixtures hold outputs only and stay small.
+
+Cases
+  tiny_init     d=128 H=4 ff=256 L=2+2 S=299 T=64 B=4   seeded init
+  tiny_trained  same model overfit on 10 synthetic drawings (weights committed as fp16)
+  config1_init  BASELINE config 1: d=256 H=8 ff=1024 L=2+2 S=1199 T=128 B=4, seeded init
+  config2_init  BASELINE config 2 model (d=512, 6+6) at B=2, S=512, T=256, seeded init
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+warnings.filterwarnings('ignore')
+
+from plankassembly_b200 import synthetic as syn  # noqa: E402
+from plankassembly.models import build_model     # noqa: E402  (the reference)
+
+GRAD_FULL = ['switch_head.weight', 'query_coord_embedding.weight', 'decoder.norm.weight',
+             'encoder.layers.0.norm1.weight', 'decoder.layers.0.multihead_attn.in_proj_bias']
+
+
+def ref_train_record(ref, batch):
+    ref.train()
+    ref.zero_grad(set_to_none=True)
+    inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
+    x = ref._embed_input(inputs)
+    y = ref._embed_output(batch['output_value'][:, :-1])
+    memory = ref.encoder(x, src_key_padding_mask=batch['input_mask'])
+    tgt_mask = ref._generate_square_subsequent_mask(y.size(1))
+    hiddens = ref.decoder(y, memory, tgt_mask=tgt_mask, tgt_key_padding_mask=batch['output_mask'],
+                          memory_key_padding_mask=batch['input_mask'])
+    dists = ref._create_dist(hiddens)
+    out = ref(batch)                         # the public path: loss + accuracy
+    out['loss'].backward()
+    n_valid = int((~batch['input_mask'][0]).sum())
+    rec = {
+        'loss': np.float64(out['loss'].item()),
+        'accuracy': np.float64(float(out['accuracy'])),
+        'dists0': dists[0].detach().numpy(),
+        'hiddens0': hiddens[0].detach().numpy(),
+        'memory0_valid': memory[0, :n_valid].detach().numpy(),
+        'embed_in0': x[0].detach().numpy(),
+        'embed_out0': y[0].detach().numpy(),
+    }
+    names, norms, sums = [], [], []
+    for n, p in ref.named_parameters():
+        names.append(n)
+        norms.append(p.grad.double().norm().item())
+        sums.append(p.grad.double().sum().item())
+        if n in GRAD_FULL:
+            rec['grad:' + n] = p.grad.numpy().copy()
+    rec['grad_names'] = np.array(names)
+    rec['grad_norms'] = np.array(norms)
+    rec['grad_sums'] = np.array(sums)
+    return rec
+
+
+@torch.no_grad()
+def ref_decode_record(ref, batch):
+    """Reference eval_step plus, per step, the relative top-1/top-2 margin of the sampled row
+    (re-derived with the reference's own methods so flips can be judged against it)."""
+    ref.eval()
+    out = ref(batch)
+    samples, attach = out['samples'], out['attach']
+    inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
+    memory = ref.encoder(ref._embed_input(inputs), src_key_padding_mask=batch['input_mask'])
+    n = samples.shape[1]
+    margins = np.zeros((samples.shape[0], n), dtype=np.float32)
+    for t in range(n):
+        prefix = samples[:, :t]
+        tgt_mask = ref._generate_square_subsequent_mask(t + 1)
+        h = ref.decoder(ref._embed_output(prefix), memory, tgt_mask=tgt_mask,
+                        memory_key_padding_mask=batch['input_mask'])
+        top2 = ref._create_dist(h)[:, -1].topk(2, -1).values
+        margins[:, t] = ((top2[:, 0] - top2[:, 1]) / top2[:, 0]).numpy()
+    return {'samples': samples.numpy(), 'attach': attach.numpy(), 'margins': margins,
+            'n_predicts': np.array([len(p) for p in out['predicts']])}
+
+
+def train_tiny(cfg, n_samples=10, steps=1500, lr=1e-3):
+    """Overfit the reference model on 10 synthetic drawings (BASELINE config-1 recipe) so that
+    decode distributions are peaked and token-exact parity is meaningful."""
+    torch.manual_seed(2022)
+    ref = build_model(cfg)
+    ref.load_state_dict(syn.init_state_dict(cfg))
+    batch = syn.batch_for(cfg, range(n_samples))
+    opt = torch.optim.Adam(ref.parameters(), lr=lr)
+    ref.train()
+    t0 = time.time()
+    for step in range(steps):
+        opt.zero_grad(set_to_none=True)
+        out = ref(batch)
+        out['loss'].backward()
+        opt.step()
+        if step % 50 == 0 or step == steps - 1:
+            print(f'  train step {step:4d} loss {out["loss"].item():.4f} acc {float(out["accuracy"]):.4f} '
+                  f'({time.time() - t0:.0f}s)', flush=True)
+        if float(out['accuracy']) >= 0.9999 and out['loss'].item() < 0.02:
+            print(f'  converged at step {step}')
+            break
+    return {k: v.detach().half() for k, v in ref.state_dict().items()}
+
+
+def run_case(name, cfg, sd, indices, out_dir, decode=True):
+    ref = build_model(cfg)
+    ref.load_state_dict(sd)
+    batch = syn.batch_for(cfg, indices)
+    t0 = time.time()
+    rec = ref_train_record(ref, batch)
+    if decode:
+        rec.update({'dec:' + k: v for k, v in ref_decode_record(ref, batch).items()})
+    rec['indices'] = np.array(list(indices))
+    np.savez_compressed(os.path.join(out_dir, name + '.npz'), **rec)
+    print(f'{name}: loss {rec["loss"]:.6f} acc {rec["accuracy"]:.4f} '
+          + (f'decode len {rec["dec:samples"].shape[1]} min margin {rec["dec:margins"].min():.2e} ' if decode else '')
+          + f'({time.time() - t0:.0f}s)', flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
+    ap.add_argument('--skip-train', action='store_true')
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+
+    tiny = syn.tiny_cfg()
+    run_case('tiny_init', tiny, syn.init_state_dict(tiny), range(4), args.out)
+
+    wpath = os.path.join(args.out, 'tiny_trained_weights_fp16.npz')
+    if not (args.skip_train and os.path.exists(wpath)):
+        sd16 = train_tiny(tiny)
+        np.savez_compressed(wpath, **{k: v.numpy() for k, v in sd16.items()})
+    sd = {k: torch.from_numpy(v).float() for k, v in np.load(wpath).items()}
+    run_case('tiny_trained', tiny, sd, range(10), args.out)
+    # held-out + noisy drawings through the trained model (BASELINE config 5 shape)
+    ref = build_model(tiny); ref.load_state_dict(sd)
+    for ratio in (0.0, 0.05, 0.10, 0.20):
+        batch = syn.batch_for(tiny, range(100, 108), noise_ratio=ratio)
+        rec = ref_decode_record(ref, batch)
+        np.savez_compressed(os.path.join(args.out, f'tiny_trained_noise{int(ratio * 100):02d}.npz'), **rec)
+        print(f'noise {ratio}: decode len {rec["samples"].shape[1]} min margin {rec["margins"].min():.2e}')
+
+    c1 = syn.config1()
+    run_case('config1_init', c1, syn.init_state_dict(c1), range(4), args.out)
+    c2 = syn.config2(dropout=0.0)
+    run_case('config2_init', c2, syn.init_state_dict(c2), range(2), args.out)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,62 @@
+"""Shared helpers for the parity tests: golden fixtures + seeded weights/batches."""
+import os
+
+import numpy as np
+import torch
+
+from plankassembly_b200 import synthetic as syn
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+CASES = {
+    'tiny_init': (syn.tiny_cfg, 'init'),
+    'tiny_trained': (syn.tiny_cfg, 'trained'),
+    'config1_init': (syn.config1, 'init'),
+    'config2_init': (lambda: syn.config2(dropout=0.0), 'init'),
+}
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def trained_tiny_state_dict():
+    z = np.load(os.path.join(GOLDEN, 'tiny_trained_weights_fp16.npz'))
+    return {k: torch.from_numpy(z[k]).float() for k in z.files}
+
+
+def case(name):
+    """-> (cfg, state_dict, batch, golden record) for a named fixture."""
+    mk, kind = CASES[name]
+    cfg = mk()
+    sd = syn.init_state_dict(cfg) if kind == 'init' else trained_tiny_state_dict()
+    g = golden(name)
+    batch = syn.batch_for(cfg, [int(i) for i in g['indices']])
+    return cfg, sd, batch, g
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def token_agreement(samples, attach, g, prefix='dec:', margin_floor=1e-4):
+    """Compare greedy tokens with the reference's.  Returns (exact, first_mismatch_info).
+    A mismatch only counts as a failure when the reference's own relative top-1/top-2 margin
+    at the first differing step of that row exceeds `margin_floor`."""
+    ref_s, ref_a, marg = g[prefix + 'samples'], g[prefix + 'attach'], g[prefix + 'margins']
+    samples, attach = np.asarray(samples), np.asarray(attach)
+    if samples.shape == ref_s.shape and (samples == ref_s).all() and (attach == ref_a).all():
+        return True, None
+    bad = []
+    n = min(samples.shape[1], ref_s.shape[1])
+    for b in range(ref_s.shape[0]):
+        diff = np.nonzero((samples[b, :n] != ref_s[b, :n]) | (attach[b, :n] != ref_a[b, :n]))[0]
+        if len(diff):
+            t = int(diff[0])
+            bad.append((b, t, float(marg[b, t])))
+    hard = [x for x in bad if x[2] > margin_floor]
+    if samples.shape != ref_s.shape and not bad:
+        hard.append(('length', samples.shape, ref_s.shape))
+    return len(hard) == 0, {'near_tie_flips': bad, 'hard': hard}

@@ -1,0 +1,84 @@
+"""Pins the oracle (oracle/plank_oracle.py) to outputs of the UNMODIFIED reference recorded by
+oracle/gen_golden.py.  CPU only.  Tolerances: 1e-3 relative is the north-star bar for
+loss/logits; the fp32 restatement is expected to sit near 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from _util import case, golden, rel_err, token_agreement, trained_tiny_state_dict
+from plank_oracle import OraclePlankModel
+from plankassembly_b200 import synthetic as syn
+
+TOL = 2e-4
+
+
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init'])
+def test_train_step_matches_reference(name):
+    cfg, sd, batch, g = case(name)
+    m = OraclePlankModel(cfg, sd, requires_grad=True)
+    m.training = True                      # dropout is 0 in these cfgs
+    out = m.train_step(batch, return_dists=True)
+    assert abs(out['loss'].item() - g['loss']) <= TOL * abs(g['loss'])
+    assert abs(float(out['accuracy']) - g['accuracy']) < 1e-6
+    assert rel_err(out['dists'][0].detach(), g['dists0']) < TOL
+    assert rel_err(out['hiddens'][0].detach(), g['hiddens0']) < TOL
+    nv = g['memory0_valid'].shape[0]
+    assert rel_err(out['memory'][0, :nv].detach(), g['memory0_valid']) < TOL
+    out['loss'].backward()
+    for n, norm, s in zip(g['grad_names'], g['grad_norms'], g['grad_sums']):
+        gr = m.P[str(n)].grad.double()
+        assert abs(gr.norm().item() - norm) <= 1e-3 * norm + 1e-9, n
+    for k in g:
+        if k.startswith('grad:'):
+            assert rel_err(m.P[k[5:]].grad, g[k]) < 1e-3, k
+
+
+def test_embeddings_match_reference():
+    cfg, sd, batch, g = case('tiny_init')
+    m = OraclePlankModel(cfg, sd)
+    assert rel_err(m.embed_input(batch)[0], g['embed_in0']) < 1e-6
+    assert rel_err(m.embed_output(batch['output_value'][:, :-1])[0], g['embed_out0']) < 1e-6
+    assert np.all(g['embed_out0'][0] == 0)          # shift-right zero row
+
+
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init'])
+def test_greedy_decode_matches_reference(name):
+    cfg, sd, batch, g = case(name)
+    m = OraclePlankModel(cfg, sd)
+    for fn in (m.eval_step_full, m.eval_step_cached):
+        out = fn(batch)
+        ok, info = token_agreement(out['samples'].numpy(), out['attach'].numpy(), g)
+        assert ok, info
+        assert [len(p) for p in out['predicts']] == list(g['dec:n_predicts']) or info is not None
+
+
+@pytest.mark.parametrize('ratio', [0, 5, 10, 20])
+def test_noisy_decode_matches_reference(ratio):
+    cfg = syn.tiny_cfg()
+    g = golden(f'tiny_trained_noise{ratio:02d}')
+    batch = syn.batch_for(cfg, range(100, 108), noise_ratio=ratio / 100)
+    out = OraclePlankModel(cfg, trained_tiny_state_dict()).eval_step_cached(batch)
+    ok, info = token_agreement(out['samples'].numpy(), out['attach'].numpy(), g, prefix='')
+    assert ok, info
+
+
+def test_pointer_mask_matches_closed_form():
+    cfg = syn.tiny_cfg()
+    m = OraclePlankModel(cfg, syn.init_state_dict(cfg))
+    pm = m.pointer_mask(20)
+    for i in range(20):
+        for j in range(20):
+            # models.py:91-101 table AND causality (eval) agree with synthetic.pointer_allowed for j<i
+            if j < i:
+                assert bool(pm[i, j]) == syn.pointer_allowed(i, j)
+
+
+def test_config2_first_rows():
+    """Full-size model (d=512, 6+6): loss + dists of sample 0 against the reference."""
+    cfg, sd, batch, g = case('config2_init')
+    m = OraclePlankModel(cfg, sd)
+    m.training = True
+    with torch.no_grad():
+        out = m.train_step(batch, return_dists=True)
+    assert abs(out['loss'].item() - g['loss']) <= TOL * abs(g['loss'])
+    assert rel_err(out['dists'][0], g['dists0']) < TOL
