@@ -1,0 +1,143 @@
+/* plank_b200 C ABI -- the drop-in boundary of the B200 hot path.
+ *
+ * The reference (manycore-research/PlankAssembly) has no FFI: its hot path is the Python
+ * surface of plankassembly/models.py and every FLOP is a PyTorch library call.  Each entry
+ * point below replaces the library op sequence issued at the cited reference line(s); the
+ * host-side mirror (plankassembly_b200/models.py) binds them through ctypes.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless the name ends in _host; the caller
+ * owns all buffers (kernels never allocate); tensors are row-major with a contiguous last
+ * dimension; ids/labels are int64 exactly as the reference's batches hold them; masks are
+ * uint8 (1 = PAD key).  `stream` is a cudaStream_t.  Return 0 on success, a negative
+ * pa_status otherwise; pa_last_error() returns a thread-local message.  No hidden syncs.
+ */
+#ifndef PLANK_B200_H
+#define PLANK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1
+#define PA_MAX_TABLES 8
+
+enum pa_status { PA_OK = 0, PA_ERR_ARG = -1, PA_ERR_CUDA = -2, PA_ERR_UNSUPPORTED = -3 };
+
+int pa_abi_version(void);
+const char* pa_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only one this library targets). */
+int pa_device_ok(void);
+
+/* ---- K1: fused input-embedding gather-sum.  Replaces models.py:103-112 (5 nn.Embedding
+ * gathers + 4 adds).  out[n,:] = sum_k tables[k][ids[k][n], :].  bwd accumulates (+=) into
+ * dtables[k] (the value table is shared with the decoder side, models.py:120). */
+int pa_embed_input_fwd(const int64_t* const* ids_host, const float* const* tables_host, int n_tables,
+                       int64_t n_tokens, int d, float* out, void* stream);
+int pa_embed_input_bwd(const float* dout, const int64_t* const* ids_host, float* const* dtables_host,
+                       const int* table_rows_host, int n_tables, int64_t n_tokens, int d, void* stream);
+
+/* ---- K2: decoder-input embedding, shifted right by one with a zero row (models.py:114-138).
+ * out[b,0,:] = 0; out[b,t,:] = e_val[value[b*ld+t-1]] + e_coord[(t-1)%dof] + e_pos[(t-1)/dof]. */
+int pa_embed_output_fwd(const int64_t* value, int64_t ld, int B, int T, int dof, const float* e_val,
+                        const float* e_coord, const float* e_pos, int d, float* out, void* stream);
+int pa_embed_output_bwd(const float* dout, const int64_t* value, int64_t ld, int B, int T, int dof,
+                        float* d_val, float* d_coord, float* d_pos, int d, void* stream);
+
+/* ---- K6/K7: y = LayerNorm_eps(x + dropout_p(a)) -- the post-norm residual blocks of
+ * torch nn/modules/transformer.py (encoder :952-956, decoder :1144-1153) as configured by
+ * models.py:60-69 (eps = 1.0 in layers, 1e-5 in the two final norms).  a may be NULL
+ * (final norms).  s receives the pre-norm sum (saved for bwd; may alias nothing, may be NULL
+ * in inference); stats = [rows,2] (mean, rstd), may be NULL in inference. */
+int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
+                  float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* s,
+                  float* stats, void* stream);
+/* dx = grad wrt x (and wrt s); da = dropout-masked copy (may be NULL); dgamma/dbeta are
+ * accumulated (+=).  partial = workspace of pa_add_ln_bwd_workspace(rows,d) bytes. */
+size_t pa_add_ln_bwd_workspace(int64_t rows, int d);
+int pa_add_ln_bwd(const float* dy, const float* s, const float* stats, const float* gamma, float p_drop,
+                  uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, float* dgamma,
+                  float* dbeta, void* partial, void* stream);
+
+/* ---- FFN activation: z <- dropout_p(relu(z)) in place (transformer.py _ff_block). */
+int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t seed, uint64_t offset, void* stream);
+int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, void* stream);
+/* x <- dropout_p(x) in place (sub-block output dropouts are fused into pa_add_ln_*). */
+
+/* ---- K3/K4/K5: multi-head attention core (torch nn/functional.py multi_head_attention_forward
+ * as called from models.py:206,212,279,293): O = dropout(softmax(Q K^T * scale + masks)) V.
+ * q[(b*Lq+i)*ldq + h*dh + c] etc., so the packed in-proj output [B,L,3d] is consumed in place.
+ * kpm: [B,Lk] uint8, 1 = PAD key (NULL = none); causal: key j visible to query i iff j <= i.
+ * lse: [B,H,Lq] natural-log sum-exp of the masked scaled scores (saved for bwd; may be NULL).
+ * impl: 0 = fp32 SIMT (exact mode), 1 = tcgen05 TF32 tensor-core path. */
+typedef struct {
+  const float* q; const float* k; const float* v;
+  int64_t ldq, ldk, ldv;
+  float* o; int64_t ldo;
+  float* lse;
+  const uint8_t* kpm;
+  int B, H, Lq, Lk, dh;
+  int causal;
+  float scale;
+  float p_drop; uint64_t seed, offset;
+  int impl;
+} pa_attn_fwd_args;
+int pa_attn_fwd(const pa_attn_fwd_args* args, void* stream);
+
+typedef struct {
+  const float* q; const float* k; const float* v;
+  int64_t ldq, ldk, ldv;
+  const float* o; const float* d_o; int64_t ldo;
+  const float* lse;
+  float* delta;                 /* workspace [B,H,Lq] */
+  float* dq; float* dk; float* dv;
+  int64_t lddq, lddk, lddv;
+  const uint8_t* kpm;
+  int B, H, Lq, Lk, dh;
+  int causal;
+  float scale;
+  float p_drop; uint64_t seed, offset;
+  int impl;
+} pa_attn_bwd_args;
+int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
+
+/* ---- K9/K10: fused training distribution + NLL + argmax (models.py:156-166, 219-227).
+ * lv [N,V] vocab logits; lp [N,T] RAW pointer scores pf.h (the kernel applies inv_d and the
+ * 1e-6 fill of entries j >= i); sw [N] switch logits; label [N] (N = B*T, row n = b*T+i).
+ * Never materialises the [B,T,V+T] distribution.  rowstat [N,4] = (lse_v, lse_p, pi, logp).
+ * accum[3] += (sum of -logp over valid rows, #valid, #correct). */
+int pa_dist_loss_fwd(const float* lv, const float* lp, const float* sw, const int64_t* label, int B, int T,
+                     int V, int pad, float inv_d, float* rowstat, int64_t* predict, float* accum,
+                     void* stream);
+/* gout: device scalar dL/dloss.  Writes dlv [N,V], dlp [N,T] (wrt the RAW scores), dsw [N]. */
+int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const int64_t* label,
+                     const float* rowstat, const float* accum, const float* gout, int B, int T, int V,
+                     int pad, float inv_d, float* dlv, float* dlp, float* dsw, void* stream);
+/* Optional full distribution (parity tests only): dists [N, V+T] as models.py:186 builds it. */
+int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
+                       float* dists, void* stream);
+
+/* ---- K11/K12: KV-cached greedy decode step pieces (replace the O(T^3) loop models.py:284-307).
+ * All state lives in caller-owned device buffers; `t` is the 0-based step. */
+int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, int dof, const float* e_val,
+                    const float* e_coord, const float* e_pos, int d, float* y, void* stream);
+/* Self-attention for the new position: appends k_new/v_new ([B,ld_new]) at slot t of the caches
+ * (cache_len rows of stride ld_cache per sequence) and attends over slots 0..len-1 (len = t+1).
+ * Cross-attention: pass k_new = NULL, len = S and kpm ([B,len]). */
+int pa_decode_attn(const float* q, int64_t ldq, const float* k_new, const float* v_new, int64_t ld_new,
+                   float* k_cache, float* v_cache, int64_t cache_len, int64_t ld_cache, int t, int len,
+                   const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream);
+/* Heads + eval distribution + sampling for step t (models.py:168-186, 235-256).
+ * h [B,d] final-normed hidden (also stored into hfin[:,t,:]); lv [B,V]; pf [B,d]; sw [B].
+ * Writes samples[b*ld+t], attach[b*ld+t]; first_end[b] = min(first_end[b], t) when the emitted
+ * token is END (the host derives the reference's stop step, models.py:306, as max_b first_end). */
+int pa_decode_head(const float* h, const float* lv, const float* pf, const float* sw, float* hfin,
+                   int64_t Tmax, int B, int d, int V, int t, int end_token, int64_t* samples,
+                   int64_t* attach, int64_t ld, int32_t* first_end, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANK_B200_H */

@@ -1,0 +1,242 @@
+// K6/K7 epilogues: y = LayerNorm_eps(x + dropout_p(a)), forward and backward, plus the FFN
+// relu+dropout elementwise kernel.  HBM-bound: one warp owns a row, 16-byte accesses, the row
+// lives in registers between the two reductions (single pass over HBM).
+//   Reference: post-norm blocks of torch nn/modules/transformer.py (:952-956, :1144-1153) with the
+//   eps = 1.0 quirk introduced at ref models.py:60-61,66-67; final norms (eps 1e-5) at :62,:68.
+// Algorithmic bytes per row: fwd reads 2*d*4 (x, a) and writes 2*d*4 (y, s) + 8; bwd reads 2*d*4
+// (dy, s) and writes up to 2*d*4 (dx, da).
+#include "common.cuh"
+
+constexpr int kLnWarps = 4;
+constexpr int kLnMaxBlocks = kNumSMs * 4;
+
+template <int NV>  // float4 per lane; d = NV*128
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a,
+                                                                     const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                                                     float eps, float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
+                                                                     float4* __restrict__ y, float4* __restrict__ s_out, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = NV * 32;
+  const float inv_d = 1.f / (float)(NV * 128);
+  const uint32_t thr = drop_threshold(p_drop);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = lane + i * 32;
+      v[i] = __ldg(x + row * d4 + c);
+      if (a != nullptr) {
+        float4 av = __ldg(a + row * d4 + c);
+        if (p_drop > 0.f) {
+          uint4 r = philox4x32(seed, (uint64_t)(row * d4 + c), offset);
+          av.x = r.x >= thr ? av.x * keep_scale : 0.f;
+          av.y = r.y >= thr ? av.y * keep_scale : 0.f;
+          av.z = r.z >= thr ? av.z * keep_scale : 0.f;
+          av.w = r.w >= thr ? av.w * keep_scale : 0.f;
+        }
+        v[i].x += av.x; v[i].y += av.y; v[i].z += av.z; v[i].w += av.w;
+      }
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = lane + i * 32;
+      if (s_out != nullptr) s_out[row * d4 + c] = v[i];
+      float4 g = __ldg(gamma + c), b = __ldg(beta + c), o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      y[row * d4 + c] = o;
+    }
+    if (stats != nullptr && lane == 0) stats[row] = make_float2(mean, rstd);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ s,
+                                                                     const float2* __restrict__ stats, const float4* __restrict__ gamma,
+                                                                     float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
+                                                                     float4* __restrict__ dx, float4* __restrict__ da, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = NV * 32, d = NV * 128;
+  const float inv_d = 1.f / (float)d;
+  const uint32_t thr = drop_threshold(p_drop);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
+    const float2 st = __ldg(stats + row);
+    float4 g[NV], xh[NV];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = lane + i * 32;
+      float4 dyv = __ldg(dy + row * d4 + c), sv = __ldg(s + row * d4 + c), gm = __ldg(gamma + c);
+      xh[i].x = (sv.x - st.x) * st.y; xh[i].y = (sv.y - st.x) * st.y; xh[i].z = (sv.z - st.x) * st.y; xh[i].w = (sv.w - st.x) * st.y;
+      g[i].x = dyv.x * gm.x; g[i].y = dyv.y * gm.y; g[i].z = dyv.z * gm.z; g[i].w = dyv.w * gm.w;
+      dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
+      db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
+      c1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      c2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+    c1 = warp_sum(c1) * inv_d;
+    c2 = warp_sum(c2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = lane + i * 32;
+      float4 o;
+      o.x = st.y * (g[i].x - c1 - xh[i].x * c2);
+      o.y = st.y * (g[i].y - c1 - xh[i].y * c2);
+      o.z = st.y * (g[i].z - c1 - xh[i].z * c2);
+      o.w = st.y * (g[i].w - c1 - xh[i].w * c2);
+      dx[row * d4 + c] = o;
+      if (da != nullptr) {
+        if (p_drop > 0.f) {
+          uint4 r = philox4x32(seed, (uint64_t)(row * d4 + c), offset);
+          o.x = r.x >= thr ? o.x * keep_scale : 0.f;
+          o.y = r.y >= thr ? o.y * keep_scale : 0.f;
+          o.z = r.z >= thr ? o.z * keep_scale : 0.f;
+          o.w = r.w >= thr ? o.w * keep_scale : 0.f;
+        }
+        da[row * d4 + c] = o;
+      }
+    }
+  }
+  // block reduce the per-warp gamma/beta partials -> partial[block][2][d]
+  __shared__ float4 sm[kLnWarps][2][NV * 32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { sm[warp][0][lane + i * 32] = dg[i]; sm[warp][1][lane + i * 32] = db[i]; }
+  __syncthreads();
+  float4* out = reinterpret_cast<float4*>(partial) + (int64_t)blockIdx.x * 2 * d4;
+  for (int i = threadIdx.x; i < 2 * d4; i += blockDim.x) {
+    int which = i / d4, c = i % d4;
+    float4 acc = sm[0][which][c];
+#pragma unroll
+    for (int w = 1; w < kLnWarps; ++w) {
+      float4 t = sm[w][which][c];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    out[i] = acc;
+  }
+}
+
+// dgamma/dbeta += sum over blocks of partial
+__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * d) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * 2 * d + i];
+  if (i < d) dgamma[i] += acc; else dbeta[i - d] += acc;
+}
+
+static int ln_grid(int64_t rows) {
+  int64_t nb = (rows + kLnWarps - 1) / kLnWarps;
+  return (int)(nb < kLnMaxBlocks ? nb : kLnMaxBlocks);
+}
+
+extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 2 * d * sizeof(float); }
+
+extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
+                             float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* s,
+                             float* stats, void* stream) {
+  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && p_drop >= 0.f && p_drop < 1.f);
+  if (rows == 0) return PA_OK;
+  int grid = ln_grid(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(NV)                                                                                                   \
+  add_ln_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)x, (const float4*)a, (const float4*)gamma,     \
+                                                         (const float4*)beta, eps, p_drop, seed, offset, rows,          \
+                                                         (float4*)y, (float4*)s, (float2*)stats)
+  switch (d / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 4: LAUNCH(4); break;
+    case 8: LAUNCH(8); break;
+    default: pa_set_error("pa_add_ln_fwd: d=%d unsupported (128,256,512,1024)", d); return PA_ERR_UNSUPPORTED;
+  }
+#undef LAUNCH
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+extern "C" int pa_add_ln_bwd(const float* dy, const float* s, const float* stats, const float* gamma, float p_drop,
+                             uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, float* dgamma,
+                             float* dbeta, void* partial, void* stream) {
+  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr);
+  if (rows == 0) return PA_OK;
+  int grid = ln_grid(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(NV)                                                                                                   \
+  add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)s, (const float2*)stats,    \
+                                                         (const float4*)gamma, p_drop, seed, offset, rows, (float4*)dx, \
+                                                         (float4*)da, (float*)partial)
+  switch (d / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 4: LAUNCH(4); break;
+    case 8: LAUNCH(8); break;
+    default: pa_set_error("pa_add_ln_bwd: d=%d unsupported", d); return PA_ERR_UNSUPPORTED;
+  }
+#undef LAUNCH
+  PA_CHECK_LAUNCH();
+  ln_param_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(float4* __restrict__ z, int64_t n4, float p_drop, uint64_t seed, uint64_t offset) {
+  const uint32_t thr = drop_threshold(p_drop);
+  const float ks = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = z[i];
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    if (p_drop > 0.f) {
+      uint4 r = philox4x32(seed, (uint64_t)i, offset);
+      v.x = r.x >= thr ? v.x * ks : 0.f; v.y = r.y >= thr ? v.y * ks : 0.f;
+      v.z = r.z >= thr ? v.z * ks : 0.f; v.w = r.w >= thr ? v.w * ks : 0.f;
+    }
+    z[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float4* __restrict__ out, float4* __restrict__ g, int64_t n4, float ks) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 o = __ldg(out + i), v = g[i];
+    v.x = o.x > 0.f ? v.x * ks : 0.f; v.y = o.y > 0.f ? v.y * ks : 0.f;
+    v.z = o.z > 0.f ? v.z * ks : 0.f; v.w = o.w > 0.f ? v.w * ks : 0.f;
+    g[i] = v;
+  }
+}
+
+extern "C" int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+  PA_CHECK_ARG(n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f);
+  if (n == 0) return PA_OK;
+  int64_t n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+  relu_dropout_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)z, n4, p_drop, seed, offset);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+extern "C" int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, void* stream) {
+  PA_CHECK_ARG(n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f);
+  if (n == 0) return PA_OK;
+  int64_t n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+  relu_dropout_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, n4, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}

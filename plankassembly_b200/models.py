@@ -1,0 +1,242 @@
+"""B200-native drop-in for the reference's ``plankassembly/models.py``.
+
+Same public surface (ref models.py:11-343): ``build_model(cfg)``, ``PlankModel.forward(batch)``
+returning ``{'loss','accuracy'}`` in train mode and ``{'samples','attach','predicts',
+'groundtruths'}`` in eval mode, ``train_step`` / ``eval_step`` / ``parse_sequence``, the attributes
+the Lightning module touches (``token``, ``vocab_size``, ``max_output_length``, ``num_output_dof``)
+and the reference's exact ``state_dict`` names/shapes, so its checkpoints load unchanged.
+
+What differs is underneath: no nn.Transformer.  Every op on the path is a hand-written sm_100a
+kernel behind the C ABI of include/plank_b200.h (embedding gather-sum, attention, residual+dropout
++LayerNorm, pointer-head distribution/loss), the dense projections go through ``linear`` (see
+``gemm.py``), and eval mode runs a KV-cached greedy decoder (``decode.py``) instead of the
+reference's O(T^3) recompute loop.  There is no CPU path: tensors must live on a B200.
+
+Reproduced quirks: the reference passes ``normalize_before`` into the
+``layer_norm_eps`` slot of nn.Transformer*Layer (ref models.py:60-61,66-67), so layers are
+POST-norm with eps = float(normalize_before) (1.0 for the shipped configs) while the two final
+norms use 1e-5; the pointer head scores against the decoder's own hidden states and divides by d.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .decode import GreedyDecoder
+
+
+class _AttnParams(nn.Module):
+    """Parameter container named like nn.MultiheadAttention (in_proj_weight/bias, out_proj.*)."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _EncoderLayerParams(nn.Module):
+    def __init__(self, d, ff):
+        super().__init__()
+        self.self_attn = _AttnParams(d)
+        self.linear1 = nn.Linear(d, ff)
+        self.linear2 = nn.Linear(ff, d)
+        self.norm1 = nn.LayerNorm(d)
+        self.norm2 = nn.LayerNorm(d)
+
+
+class _DecoderLayerParams(nn.Module):
+    def __init__(self, d, ff):
+        super().__init__()
+        self.self_attn = _AttnParams(d)
+        self.multihead_attn = _AttnParams(d)
+        self.linear1 = nn.Linear(d, ff)
+        self.linear2 = nn.Linear(ff, d)
+        self.norm1 = nn.LayerNorm(d)
+        self.norm2 = nn.LayerNorm(d)
+        self.norm3 = nn.LayerNorm(d)
+
+
+class _Stack(nn.Module):
+    def __init__(self, layers, norm):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.norm = norm
+
+
+class PlankModel(nn.Module):
+
+    def __init__(self, num_model=512, num_head=8, num_feedforward=1024, dropout=0.1, activation="relu",
+                 normalize_before=True, num_encoder_layers=6, num_decoder_layers=6, num_view=3, num_type=2,
+                 num_input_dof=4, num_output_dof=6, max_input_length=400, max_output_length=128,
+                 vocab_size=514, token=None):
+        super().__init__()
+        if activation != 'relu':
+            raise NotImplementedError('only the relu FFN of the shipped configs is implemented')
+        if num_model % 128 or (num_model // num_head) not in (32, 64):
+            raise NotImplementedError('kernels are built for d % 128 == 0 and head dim 32 or 64')
+        max_num_input = math.ceil(max_input_length / num_input_dof)
+        max_num_output = math.ceil(max_output_length / num_output_dof)
+        self.num_model, self.num_head = num_model, num_head
+        self.max_num_input, self.max_input_length = max_num_input, max_input_length
+        self.max_output_length, self.max_num_output = max_output_length, max_num_output
+        self.num_input_dof, self.num_output_dof = num_input_dof, num_output_dof
+        self.vocab_size = vocab_size
+        self.token = token
+        self.dropout = float(dropout)
+        # the positional-argument quirk of ref models.py:60-61: eps := normalize_before, post-norm
+        self.layer_eps = float(normalize_before)
+        # 'simt' = fp32 CUDA-core attention (exact), 'tc' = tcgen05 TF32 attention forward
+        self.attn_impl = os.environ.get('PLANK_B200_ATTN', 'simt')
+
+        self.input_embeddings = nn.ModuleDict({
+            'input_value': nn.Embedding(vocab_size, num_model),
+            'input_pos': nn.Embedding(max_num_input, num_model),
+            'input_coord': nn.Embedding(num_input_dof, num_model),
+            'input_view': nn.Embedding(num_view, num_model),
+            'input_type': nn.Embedding(num_type, num_model),
+        })
+        self.query_coord_embedding = nn.Embedding(num_output_dof, num_model)
+        self.query_pos_embedding = nn.Embedding(max_num_output, num_model)
+        self.encoder = _Stack([_EncoderLayerParams(num_model, num_feedforward) for _ in range(num_encoder_layers)],
+                              nn.LayerNorm(num_model) if normalize_before else None)
+        self.decoder = _Stack([_DecoderLayerParams(num_model, num_feedforward) for _ in range(num_decoder_layers)],
+                              nn.LayerNorm(num_model))
+        self.vocab_head = nn.Linear(num_model, vocab_size)
+        self.pointer_head = nn.Linear(num_model, num_model)
+        self.switch_head = nn.Linear(num_model, 1)
+        self._reset_parameters()
+        self._decoder_engine = None
+
+    def _reset_parameters(self):
+        """Xavier-uniform on every tensor with dim > 1, embeddings included (ref models.py:78-83)."""
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    # ------------------------------------------------------------------ building blocks
+    def _p(self):
+        return self.dropout if self.training else 0.0
+
+    def _impl(self):
+        return ops.ATTN_IMPL[self.attn_impl]
+
+    @staticmethod
+    def _kpm(mask):
+        return mask.contiguous().view(torch.uint8)
+
+    def _embed_input(self, inputs):
+        keys = [k for k in inputs if 'mask' not in k]
+        ids = [inputs[k] for k in keys]
+        tables = [self.input_embeddings[k].weight for k in keys]
+        return ops.EmbedInput.apply(len(keys), *ids, *tables)
+
+    def _embed_output(self, output_value, T):
+        """Embeds output_value[:, :T-1] behind a zero row -> [B,T,d] (ref models.py:114-138)."""
+        return ops.EmbedOutput.apply(output_value, T, self.num_output_dof, self.input_embeddings['input_value'].weight,
+                                     self.query_coord_embedding.weight, self.query_pos_embedding.weight)
+
+    def _ffn(self, layer, x):
+        h = F.linear(x, layer.linear1.weight, layer.linear1.bias)
+        h = ops.ReluDropout.apply(h, self._p())
+        return F.linear(h, layer.linear2.weight, layer.linear2.bias)
+
+    def _encode(self, x, in_kpm):
+        p, H = self._p(), self.num_head
+        for layer in self.encoder.layers:
+            sa = layer.self_attn
+            qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+            a = ops.SelfAttention.apply(qkv, in_kpm, H, False, p, self._impl())
+            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            x = ops.AddLayerNorm.apply(x, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
+            x = ops.AddLayerNorm.apply(x, self._ffn(layer, x), layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
+        if self.encoder.norm is not None:
+            x = ops.AddLayerNorm.apply(x, None, self.encoder.norm.weight, self.encoder.norm.bias, 1e-5, 0.0)
+        return x
+
+    def _decode_train(self, y, memory, in_kpm, out_kpm):
+        p, H, d = self._p(), self.num_head, self.num_model
+        for layer in self.decoder.layers:
+            sa, ca = layer.self_attn, layer.multihead_attn
+            qkv = F.linear(y, sa.in_proj_weight, sa.in_proj_bias)
+            a = ops.SelfAttention.apply(qkv, out_kpm, H, True, p, self._impl())
+            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            y = ops.AddLayerNorm.apply(y, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
+            q = F.linear(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
+            kv = F.linear(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:])
+            a = ops.CrossAttention.apply(q, kv, in_kpm, H, p, self._impl())
+            a = F.linear(a, ca.out_proj.weight, ca.out_proj.bias)
+            y = ops.AddLayerNorm.apply(y, a, layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
+            y = ops.AddLayerNorm.apply(y, self._ffn(layer, y), layer.norm3.weight, layer.norm3.bias, self.layer_eps, p)
+        return ops.AddLayerNorm.apply(y, None, self.decoder.norm.weight, self.decoder.norm.bias, 1e-5, 0.0)
+
+    def _heads(self, h):
+        lv = F.linear(h, self.vocab_head.weight, self.vocab_head.bias)
+        pf = F.linear(h, self.pointer_head.weight, self.pointer_head.bias)
+        lp = torch.bmm(pf, h.transpose(1, 2))                      # raw scores; 1/d applied in the kernel
+        sw = F.linear(h, self.switch_head.weight, self.switch_head.bias).squeeze(-1)
+        return lv, lp, sw
+
+    # ------------------------------------------------------------------ ref models.py:190-233
+    def train_step(self, batch, return_dists=False):
+        inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
+        in_kpm = self._kpm(batch['input_mask'])
+        out_kpm = self._kpm(batch['output_mask'])
+        output_value, output_label = batch['output_value'], batch['output_label']
+        T = output_value.shape[1]
+
+        x = self._embed_input(inputs)
+        y = self._embed_output(output_value, T)
+        memory = self._encode(x, in_kpm)
+        hiddens = self._decode_train(y, memory, in_kpm, out_kpm)
+        lv, lp, sw = self._heads(hiddens)
+        loss, accuracy, predict = ops.DistLoss.apply(lv, lp, sw, output_label, self.token.PAD, 1.0 / self.num_model)
+        rets = {'loss': loss, 'accuracy': accuracy}
+        if return_dists:                                           # parity tests only
+            rets.update(dists=ops.dist_train_full(lv, lp, sw, 1.0 / self.num_model), hiddens=hiddens, memory=memory,
+                        predict=predict)
+        return rets
+
+    # ------------------------------------------------------------------ ref models.py:258-323
+    def parse_sequence(self, sequence):
+        valid_mask = torch.cumsum(sequence == self.token.END, 0) == 0
+        valid_seq = sequence[valid_mask]
+        num_plank = len(valid_seq) // self.num_output_dof
+        return valid_seq[:num_plank * self.num_output_dof].reshape(-1, self.num_output_dof)
+
+    @torch.no_grad()
+    def eval_step(self, batch):
+        """Greedy decoding with persistent K/V caches (same tokens as ref models.py:267-323)."""
+        inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
+        in_kpm = self._kpm(batch['input_mask'])
+        memory = self._encode(self._embed_input(inputs), in_kpm)
+        if self._decoder_engine is None:
+            self._decoder_engine = GreedyDecoder(self)
+        output, attach = self._decoder_engine.run(memory, in_kpm)
+        predicts, groundtruths = [], []
+        for i in range(output.shape[0]):
+            predicts.append(self.parse_sequence(output[i]))
+            groundtruths.append(self.parse_sequence(batch['output_value'][i]))
+        return {'samples': output, 'attach': attach, 'predicts': predicts, 'groundtruths': groundtruths}
+
+    def forward(self, batch):
+        return self.train_step(batch) if self.training else self.eval_step(batch)
+
+
+def build_model(cfg):
+    """Same positional field order as ref models.py:333-343."""
+    return PlankModel(
+        cfg.MODEL.NUM_MODEL, cfg.MODEL.NUM_HEAD,
+        cfg.MODEL.NUM_FEEDFORWARD, cfg.MODEL.DROPOUT,
+        cfg.MODEL.ACTIVATION, cfg.MODEL.NORMALIZE_BEFORE,
+        cfg.MODEL.NUM_ENCODER_LAYERS, cfg.MODEL.NUM_DECODER_LAYERS,
+        cfg.DATA.NUM_VIEW, cfg.DATA.NUM_TYPE,
+        cfg.DATA.NUM_INPUT_DOF, cfg.DATA.NUM_OUTPUT_DOF,
+        cfg.DATA.MAX_INPUT_LENGTH, cfg.DATA.MAX_OUTPUT_LENGTH,
+        cfg.DATA.VOCAB_SIZE, cfg.TOKEN)

@@ -1,0 +1,296 @@
+"""torch.autograd wrappers over the C-ABI kernels (include/plank_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every op below
+runs a hand-written sm_100a kernel through ctypes.  All tensors are fp32 CUDA tensors; ids stay
+int64 as the reference's batches hold them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import AttnBwdArgs, AttnFwdArgs, call
+
+ATTN_IMPL = {'simt': 0, 'tc': 1}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PlankB200Error('plankassembly_b200 ops need CUDA tensors (no CPU fallback); '
+                                      'move the model and batch to a B200 device')
+
+
+class DropoutState:
+    """Seed + per-site Philox offsets.  Every dropout site of every forward draws a fresh offset;
+    backward kernels regenerate the masks from (seed, offset)."""
+
+    def __init__(self):
+        self.seed = None
+        self.counter = 0
+
+    def next(self):
+        if self.seed is None:
+            self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        self.counter += 1
+        return self.seed, self.counter
+
+
+RNG = DropoutState()
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+class EmbedInput(Function):
+    """K1 (ref models.py:103-112)."""
+
+    @staticmethod
+    def forward(ctx, n_tables, *args):
+        ids, tables = args[:n_tables], args[n_tables:]
+        _require_cuda(*ids, *tables)
+        ids = [i.contiguous() for i in ids]
+        B, S = ids[0].shape
+        d = tables[0].shape[1]
+        out = torch.empty(B, S, d, device=tables[0].device, dtype=torch.float32)
+        call('pa_embed_input_fwd', _ptr_array([i.data_ptr() for i in ids]), _ptr_array([t.data_ptr() for t in tables]),
+             n_tables, B * S, d, out.data_ptr(), _stream())
+        ctx.ids = ids
+        ctx.shapes = [t.shape for t in tables]
+        ctx.n = n_tables
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes]
+        rows = (C.c_int * ctx.n)(*[s[0] for s in ctx.shapes])
+        B, S = ctx.ids[0].shape
+        call('pa_embed_input_bwd', dout.data_ptr(), _ptr_array([i.data_ptr() for i in ctx.ids]),
+             _ptr_array([g.data_ptr() for g in grads]), rows, ctx.n, B * S, dout.shape[-1], _stream())
+        return (None, *([None] * ctx.n), *grads)
+
+
+class EmbedOutput(Function):
+    """K2 (ref models.py:114-138): value[:, :T-1] shifted right by one behind a zero row."""
+
+    @staticmethod
+    def forward(ctx, value, T, dof, e_val, e_coord, e_pos):
+        _require_cuda(value, e_val)
+        assert value.stride(1) == 1
+        B, d = value.shape[0], e_val.shape[1]
+        out = torch.empty(B, T, d, device=e_val.device, dtype=torch.float32)
+        call('pa_embed_output_fwd', value.data_ptr(), value.stride(0), B, T, dof, e_val.data_ptr(), e_coord.data_ptr(),
+             e_pos.data_ptr(), d, out.data_ptr(), _stream())
+        ctx.value, ctx.T, ctx.dof = value, T, dof
+        ctx.shapes = (e_val.shape, e_coord.shape, e_pos.shape)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        gv, gc, gp = (torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes)
+        call('pa_embed_output_bwd', dout.data_ptr(), ctx.value.data_ptr(), ctx.value.stride(0), dout.shape[0], ctx.T,
+             ctx.dof, gv.data_ptr(), gc.data_ptr(), gp.data_ptr(), dout.shape[-1], _stream())
+        return None, None, None, gv, gc, gp
+
+
+class AddLayerNorm(Function):
+    """y = LayerNorm_eps(x + dropout_p(a)); a may be None (final norms)."""
+
+    @staticmethod
+    def forward(ctx, x, a, gamma, beta, eps, p_drop):
+        _require_cuda(x, gamma)
+        x = x.contiguous()
+        a = a.contiguous() if a is not None else None
+        d = x.shape[-1]
+        rows = x.numel() // d
+        y = torch.empty_like(x)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad or (a is not None and a.requires_grad))
+        s = torch.empty_like(x) if (need_grad and a is not None) else None
+        stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
+        seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
+        call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
+             seed, off, rows, d, y.data_ptr(), _ptr(s), _ptr(stats), _stream())
+        ctx.save_for_backward(s if s is not None else x, stats, gamma)
+        ctx.has_a, ctx.p, ctx.seed, ctx.off = a is not None, (p_drop if a is not None else 0.0), seed, off
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        s, stats, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        d = s.shape[-1]
+        rows = s.numel() // d
+        dx = torch.empty_like(s)
+        da = torch.empty_like(s) if (ctx.has_a and ctx.p > 0) else None
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=s.device, dtype=torch.uint8)
+        call('pa_add_ln_bwd', dy.data_ptr(), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed, ctx.off,
+             rows, d, dx.data_ptr(), _ptr(da), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _stream(), launches=2)
+        if ctx.has_a and da is None:
+            da = dx                      # no dropout: same gradient flows to both summands
+        return dx, (da if ctx.has_a else None), dgamma, dbeta, None, None
+
+
+class ReluDropout(Function):
+    """z <- dropout_p(relu(z)) in place (FFN activation, torch transformer.py _ff_block)."""
+
+    @staticmethod
+    def forward(ctx, z, p_drop):
+        _require_cuda(z)
+        assert z.is_contiguous()
+        seed, off = RNG.next() if p_drop > 0 else (0, 0)
+        call('pa_relu_dropout_fwd', z.data_ptr(), z.numel(), p_drop, seed, off, _stream())
+        ctx.mark_dirty(z)
+        ctx.save_for_backward(z)
+        ctx.p = p_drop
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        g = g.contiguous().clone()
+        call('pa_relu_dropout_bwd', out.data_ptr(), g.data_ptr(), g.numel(), ctx.p, _stream())
+        return g, None
+
+
+def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, seed, off, impl, want_lse, device):
+    o = torch.empty(B, Lq, H * dh, device=device, dtype=torch.float32)
+    lse = torch.empty(B, H, Lq, device=device, dtype=torch.float32) if want_lse else None
+    a = AttnFwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), H * dh, _ptr(lse), _ptr(kpm), B, H, Lq, Lk, dh, int(causal),
+                    dh ** -0.5, p_drop, seed, off, impl)
+    call('pa_attn_fwd', C.byref(a), _stream())
+    return o, lse
+
+
+def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, B, H, Lq, Lk, dh, kpm, causal, p_drop,
+              seed, off, impl):
+    delta = torch.empty(B, H, Lq, device=o.device, dtype=torch.float32)
+    a = AttnBwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), do.data_ptr(), H * dh, lse.data_ptr(), delta.data_ptr(),
+                    dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl)
+    call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
+
+
+class SelfAttention(Function):
+    """K3/K4: attention core over the packed in-projection output qkv [B,L,3d]."""
+
+    @staticmethod
+    def forward(ctx, qkv, kpm, H, causal, p_drop, impl):
+        _require_cuda(qkv)
+        qkv = qkv.contiguous()
+        B, L, d3 = qkv.shape
+        d = d3 // 3
+        seed, off = RNG.next() if p_drop > 0 else (0, 0)
+        base = qkv.data_ptr()
+        o, lse = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
+                           impl, torch.is_grad_enabled() and qkv.requires_grad, qkv.device)
+        ctx.save_for_backward(qkv, o, lse, kpm)
+        ctx.cfg = (H, causal, p_drop, seed, off, impl)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        qkv, o, lse, kpm = ctx.saved_tensors
+        H, causal, p_drop, seed, off, impl = ctx.cfg
+        B, L, d3 = qkv.shape
+        d = d3 // 3
+        dqkv = torch.empty_like(qkv)
+        base, g = qkv.data_ptr(), dqkv.data_ptr()
+        _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
+                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, 0)
+        return dqkv, None, None, None, None, None
+
+
+class CrossAttention(Function):
+    """K5: queries q [B,Lq,d] against the packed memory projection kv [B,Lk,2d]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, kpm, H, p_drop, impl):
+        _require_cuda(q, kv)
+        q, kv = q.contiguous(), kv.contiguous()
+        B, Lq, d = q.shape
+        Lk = kv.shape[1]
+        seed, off = RNG.next() if p_drop > 0 else (0, 0)
+        kb = kv.data_ptr()
+        need = torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad)
+        o, lse = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
+                           impl, need, q.device)
+        ctx.save_for_backward(q, kv, o, lse, kpm)
+        ctx.cfg = (H, p_drop, seed, off, impl)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        q, kv, o, lse, kpm = ctx.saved_tensors
+        H, p_drop, seed, off, impl = ctx.cfg
+        B, Lq, d = q.shape
+        Lk = kv.shape[1]
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        kb, gb = kv.data_ptr(), dkv.data_ptr()
+        _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
+                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, 0)
+        return dq, dkv, None, None, None, None
+
+
+class DistLoss(Function):
+    """K9/K10 (ref models.py:156-166, 219-227): loss, accuracy and argmax without the [B,T,V+T] tensor.
+    lp holds the RAW pointer scores pf.h^T; the kernel applies 1/d and the 1e-6 fill."""
+
+    @staticmethod
+    def forward(ctx, lv, lp, sw, label, pad, inv_d):
+        _require_cuda(lv, lp, sw, label)
+        lv, lp, sw, label = lv.contiguous(), lp.contiguous(), sw.contiguous(), label.contiguous()
+        B, T, V = lv.shape
+        rowstat = torch.empty(B * T, 4, device=lv.device, dtype=torch.float32)
+        predict = torch.empty(B, T, device=lv.device, dtype=torch.int64)
+        accum = torch.zeros(3, device=lv.device, dtype=torch.float32)
+        call('pa_dist_loss_fwd', lv.data_ptr(), lp.data_ptr(), sw.data_ptr(), label.data_ptr(), B, T, V, pad, inv_d,
+             rowstat.data_ptr(), predict.data_ptr(), accum.data_ptr(), _stream())
+        loss = accum[0] / accum[1]
+        accuracy = accum[2] / (accum[1] + 1e-10)
+        ctx.save_for_backward(lv, lp, sw, label, rowstat, accum)
+        ctx.cfg = (pad, inv_d)
+        ctx.mark_non_differentiable(accuracy, predict)
+        return loss, accuracy, predict
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gloss, _gacc, _gpred):
+        lv, lp, sw, label, rowstat, accum = ctx.saved_tensors
+        pad, inv_d = ctx.cfg
+        B, T, V = lv.shape
+        dlv, dlp, dsw = torch.empty_like(lv), torch.empty_like(lp), torch.empty_like(sw)
+        gloss = gloss.contiguous().to(torch.float32)
+        call('pa_dist_loss_bwd', lv.data_ptr(), lp.data_ptr(), sw.data_ptr(), label.data_ptr(), rowstat.data_ptr(),
+             accum.data_ptr(), gloss.data_ptr(), B, T, V, pad, inv_d, dlv.data_ptr(), dlp.data_ptr(), dsw.data_ptr(), _stream())
+        return dlv, dlp, dsw, None, None, None
+
+
+def dist_train_full(lv, lp, sw, inv_d):
+    """Materialise the training distribution [B,T,V+T] (parity tests only)."""
+    B, T, V = lv.shape
+    out = torch.empty(B, T, V + T, device=lv.device, dtype=torch.float32)
+    call('pa_dist_train_full', lv.contiguous().data_ptr(), lp.contiguous().data_ptr(), sw.contiguous().data_ptr(), B, T, V,
+         inv_d, out.data_ptr(), _stream())
+    return out

@@ -1,0 +1,120 @@
+"""Whole-path parity on the GPU: PlankModel (CUDA kernels behind the C ABI) against the golden
+outputs recorded from the unmodified reference (tests/golden, oracle/gen_golden.py) and against
+the oracle on fresh seeded inputs.  Bars (BASELINE.json north_star): loss/logits within 1e-3
+relative; greedy token ids bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _util import case, golden, rel_err, token_agreement, trained_tiny_state_dict  # noqa: E402
+from plankassembly_b200 import synthetic as syn  # noqa: E402
+
+TOL = 1e-3          # north-star tolerance for logits / loss (relative, fp32)
+
+
+def to_dev(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def build(cfg, sd):
+    from plankassembly_b200.models import build_model
+    m = build_model(cfg)
+    missing = m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init'])
+def test_train_step_matches_reference(name):
+    cfg, sd, batch, g = case(name)
+    m = build(cfg, sd).train()
+    out = m.train_step(to_dev(batch), return_dists=True)
+    assert abs(out['loss'].item() - g['loss']) <= TOL * abs(g['loss'])
+    assert abs(out['accuracy'].item() - g['accuracy']) < 1e-6
+    assert rel_err(out['dists'][0].cpu(), g['dists0']) < TOL
+    assert rel_err(out['hiddens'][0].cpu(), g['hiddens0']) < TOL
+    nv = g['memory0_valid'].shape[0]
+    assert rel_err(out['memory'][0, :nv].cpu(), g['memory0_valid']) < TOL
+    out['loss'].backward()
+    grads = dict(m.named_parameters())
+    for n, norm in zip(g['grad_names'], g['grad_norms']):
+        gr = grads[str(n)].grad
+        assert gr is not None, n
+        assert abs(gr.double().norm().item() - norm) <= TOL * norm + 1e-9, (n, gr.double().norm().item(), norm)
+    for k in g:
+        if k.startswith('grad:'):
+            assert rel_err(grads[k[5:]].grad.cpu(), g[k]) < TOL, k
+
+
+def test_forward_returns_reference_shaped_dict():
+    cfg, sd, batch, g = case('tiny_init')
+    m = build(cfg, sd).train()
+    out = m(to_dev(batch))
+    assert set(out) == {'loss', 'accuracy'}
+    assert out['loss'].dim() == 0 and out['loss'].requires_grad
+    torch.mean(out['loss']); torch.mean(out['accuracy'])      # trainer_complete.py:66-67 does this
+
+
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init'])
+def test_greedy_decode_matches_reference(name):
+    cfg, sd, batch, g = case(name)
+    m = build(cfg, sd).eval()
+    out = m(to_dev(batch))
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g)
+    assert ok, info
+    if info is None:
+        assert [len(p) for p in out['predicts']] == list(g['dec:n_predicts'])
+    assert len(out['groundtruths']) == len(out['predicts']) == out['samples'].shape[0]
+
+
+@pytest.mark.parametrize('ratio', [0, 5, 10, 20])
+def test_noisy_decode_matches_reference(ratio):
+    cfg = syn.tiny_cfg()
+    g = golden(f'tiny_trained_noise{ratio:02d}')
+    batch = syn.batch_for(cfg, range(100, 108), noise_ratio=ratio / 100)
+    m = build(cfg, trained_tiny_state_dict()).eval()
+    out = m(to_dev(batch))
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='')
+    assert ok, info
+
+
+def test_missing_input_type_key():
+    """Sideface batches carry no input_type (ref trainer_sideface.py); the model must cope."""
+    from plank_oracle import OraclePlankModel
+    cfg = syn.tiny_cfg()
+    sd = syn.init_state_dict(cfg)
+    batch = syn.batch_for(cfg, range(3), with_type=False)
+    m = build(cfg, sd).train()
+    out = m(to_dev(batch))
+    o = OraclePlankModel(cfg, sd)
+    o.training = True
+    with torch.no_grad():
+        ref = o.train_step(batch)
+    assert abs(out['loss'].item() - ref['loss'].item()) <= TOL * ref['loss'].item()
+
+
+def test_dropout_training_statistics():
+    """With the configured dropout the loss is stochastic but must stay close to the dropout-free
+    loss on an untrained model, differ between calls, and give finite grads everywhere."""
+    cfg = syn.tiny_cfg(dropout=0.2)
+    sd = syn.init_state_dict(cfg)
+    batch = to_dev(syn.batch_for(cfg, range(4)))
+    m = build(cfg, sd).train()
+    l1 = m(batch)['loss']
+    l2 = m(batch)['loss']
+    assert l1.item() != l2.item()
+    g = golden('tiny_init')
+    assert abs(l1.item() - g['loss']) < 0.05 * g['loss']
+    l1.backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_cpu_tensors_fail_loudly():
+    from plankassembly_b200._lib import PlankB200Error
+    from plankassembly_b200.models import build_model
+    cfg = syn.tiny_cfg()
+    m = build_model(cfg).train()
+    with pytest.raises(PlankB200Error):
+        m(syn.batch_for(cfg, range(2)))
