@@ -103,6 +103,26 @@ typedef struct {
 } pa_attn_bwd_args;
 int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
 
+/* ---- Dense projections on the tcgen05 tensor cores (TF32 in, FP32 accumulate in TMEM):
+ *   C[M,N] = alpha * A * B^T (+ bias[N]) (relu) (dropout_p)     -- every nn.Linear on the path
+ * (in/out projections, FFN, heads: models.py:60-74,145-153) and, with the MN-major operand forms,
+ * their input/weight gradients.  a_mn = 0: A is [M,K] row-major; a_mn = 1: A is stored [K,M].
+ * b_mn = 0: B is [N,K] row-major (a torch Linear weight); b_mn = 1: B is stored [K,N].
+ * batch > 1: A/B row offsets advance by a_batch_rows/b_batch_rows, C by c_batch_stride elements
+ * (pointer scoring bmm, models.py:149).  split_k > 1 requires accumulate = 1 (C += via fp32 RED). */
+typedef struct {
+  const float* a; int64_t lda; int a_mn;
+  const float* b; int64_t ldb; int b_mn;
+  float* c; int64_t ldc;
+  const float* bias;
+  int relu; float p_drop; uint64_t seed, offset;
+  float alpha;
+  int M, N, K;
+  int batch; int64_t a_batch_rows, b_batch_rows, c_batch_stride;
+  int split_k; int accumulate;
+} pa_gemm_args;
+int pa_gemm_tf32(const pa_gemm_args* args, void* stream);
+
 /* ---- K9/K10: fused training distribution + NLL + argmax (models.py:156-166, 219-227).
  * lv [N,V] vocab logits; lp [N,T] RAW pointer scores pf.h (the kernel applies inv_d and the
  * 1e-6 fill of entries j >= i); sw [N] switch logits; label [N] (N = B*T, row n = b*T+i).

@@ -26,6 +26,13 @@ class AttnBwdArgs(C.Structure):
                 ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32)]
 
 
+class GemmArgs(C.Structure):
+    _fields_ = [('a', vp), ('lda', i64), ('a_mn', i32), ('b', vp), ('ldb', i64), ('b_mn', i32),
+                ('c', vp), ('ldc', i64), ('bias', vp), ('relu', i32), ('p_drop', f32), ('seed', u64), ('offset', u64),
+                ('alpha', f32), ('M', i32), ('N', i32), ('K', i32), ('batch', i32),
+                ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32)]
+
+
 # name -> (restype, argtypes); mirrors include/plank_b200.h one to one
 SIGNATURES = {
     'pa_abi_version': (i32, []),
@@ -42,6 +49,7 @@ SIGNATURES = {
     'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, vp]),
     'pa_attn_fwd': (i32, [C.POINTER(AttnFwdArgs), vp]),
     'pa_attn_bwd': (i32, [C.POINTER(AttnBwdArgs), vp]),
+    'pa_gemm_tf32': (i32, [C.POINTER(GemmArgs), vp]),
     'pa_dist_loss_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     'pa_dist_loss_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     'pa_dist_train_full': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),

@@ -1,0 +1,291 @@
+// Dense projections on the 5th-gen tensor cores: C = alpha * op(A) op(B)^T (+bias)(relu)(dropout),
+// TF32 inputs read straight from the fp32 tensors, FP32 accumulation in TMEM.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
+//   warp 1      MMA issuer    (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM owner
+//   warps 2..5  epilogue      (tcgen05.ld 32x32b -> bias/ReLU/Philox dropout -> 16-byte stores)
+// Three pipelines: smem full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators
+// (MMA <-> epilogue), static persistent tile schedule.
+//
+// Operand forms (all row-major fp32 in HBM):
+//   A K-major : A[M,K]   (activations x, dY)          A MN-major: stored [K,M]  (dY for dW = dY^T X)
+//   B K-major : B[N,K]   (weights W, or W^T copies)   B MN-major: stored [K,N]  (x for dW)
+// Used for: every nn.Linear on the path (ref models.py:60-74 via torch transformer.py), their
+// input/weight gradients, and the pointer scoring bmm (ref models.py:149) in batched mode.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 32;         // 32 tf32 = 128 B = one swizzle row
+constexpr int UK = 8;          // K per tcgen05.mma.kind::tf32
+constexpr int kThreads = 192;
+
+struct GemmParams {
+  float* c; int64_t ldc; int64_t c_batch_stride;
+  const float* bias;
+  int M, N, K;
+  int batch; int a_batch_rows, b_batch_rows;
+  int split_k; int accumulate;
+  int relu; float p_drop; uint64_t seed, offset;
+  float alpha;
+  int m_tiles, n_tiles;
+};
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 4;           // 16 KB
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_batch = p.m_tiles * p.n_tiles * p.split_k;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int k_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
+
+  auto decode = [&](int tile, int& b, int& mt, int& nt, int& kb0, int& kb1) {
+    b = tile / tiles_per_batch;
+    int r = tile - b * tiles_per_batch;
+    int sp = r / (p.m_tiles * p.n_tiles);
+    r -= sp * p.m_tiles * p.n_tiles;
+    nt = r / p.m_tiles;            // m fastest: CTAs running together share the B (weight) tile
+    mt = r - nt * p.m_tiles;
+    kb0 = sp * k_per_split;
+    kb1 = min(k_blocks_total, kb0 + k_per_split);
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, mt, nt, kb0, kb1;
+        decode(tile, b, mt, nt, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc::mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          tc::mbar_arrive_expect_tx(full_bar + stage, C::kStageBytes);
+          if constexpr (!A_MN) {
+            tc::tma_load_2d(sa, &tma_a, kb * BK, b * p.a_batch_rows + mt * BM, full_bar + stage);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) tc::tma_load_2d(sa + j * (BK * 128), &tma_a, mt * BM + j * 32, kb * BK, full_bar + stage);
+          }
+          if constexpr (!B_MN) {
+            tc::tma_load_2d(sb, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN, full_bar + stage);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(sb + j * (BK * 128), &tma_b, nt * BN + j * 32, b * p.b_batch_rows + kb * BK, full_bar + stage);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, mt, nt, kb0, kb1;
+        decode(tile, b, mt, nt, kb0, kb1);
+        tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          tc::mbar_wait(full_bar + stage, phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          // K-major: LBO unused, SBO = 1024 (8 rows x 128 B).  MN-major: LBO = one 32-wide MN block
+          // (BK rows x 128 B), SBO = 1024 (8 K rows).
+          const uint64_t da = tc::make_smem_desc(sa, A_MN ? BK * 128 : 16, 1024);
+          const uint64_t db = tc::make_smem_desc(sb, B_MN ? BK * 128 : 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t dak = tc::desc_advance(da, A_MN ? k * 1024 : k * UK * 4);
+            const uint64_t dbk = tc::desc_advance(db, B_MN ? k * 1024 : k * UK * 4);
+            tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc::tc_commit(empty_bar + stage);            // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::tc_commit(tmem_full + acc);                // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t thr = drop_threshold(p.p_drop);
+    const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int b, mt, nt, kb0, kb1;
+      decode(tile, b, mt, nt, kb0, kb1);
+      tc::mbar_wait(tmem_full + acc, acc_phase);
+      tc::tc_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      const bool row_ok = row < p.M && kb1 > kb0;
+      float* crow = p.c + (int64_t)b * p.c_batch_stride + (int64_t)row * p.ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
+        tc::tmem_ld_wait();
+        const int col0 = nt * BN + c0;
+        if (row_ok && col0 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = col0 + j;
+            if (col >= p.N) break;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(r[j + e]) * p.alpha;
+              if (p.bias != nullptr && col + e < p.N) x += __ldg(p.bias + col + e);
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[e] = x;
+            }
+            if (p.p_drop > 0.f) {
+              // same element -> (counter, lane) mapping as relu_dropout_fwd_kernel: float4 index of [M,N]
+              uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col) >> 2), p.offset);
+              v[0] = rn.x >= thr ? v[0] * ks : 0.f; v[1] = rn.y >= thr ? v[1] * ks : 0.f;
+              v[2] = rn.z >= thr ? v[2] * ks : 0.f; v[3] = rn.w >= thr ? v[3] * ks : 0.f;
+            }
+            if (col + 3 < p.N && ((p.ldc & 3) == 0)) {
+              float4 o = make_float4(v[0], v[1], v[2], v[3]);
+              if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + col), o);
+              else *reinterpret_cast<float4*>(crow + col) = o;
+            } else {
+              for (int e = 0; e < 4 && col + e < p.N; ++e) {
+                if (p.accumulate) atomicAdd(crow + col + e, v[e]);
+                else crow[col + e] = v[e];
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void resolve_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    g_encode = (EncodeFn)fn;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const pa_gemm_args& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
+  else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 4, 32, BK);
+  if (rc) return rc;
+  if (!B_MN) rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.N), (uint64_t)a.ldb * 4, BK, BN);
+  else rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.N, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.K), (uint64_t)a.ldb * 4, 32, BK);
+  if (rc) return rc;
+  GemmParams p{};
+  p.c = a.c; p.ldc = a.ldc; p.c_batch_stride = a.c_batch_stride; p.bias = a.bias;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch < 1 ? 1 : a.batch;
+  p.a_batch_rows = (int)a.a_batch_rows; p.b_batch_rows = (int)a.b_batch_rows;
+  p.split_k = a.split_k < 1 ? 1 : a.split_k; p.accumulate = a.accumulate;
+  p.relu = a.relu; p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset; p.alpha = a.alpha;
+  p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_done = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles * p.split_k * p.batch;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, p);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+}  // namespace
+
+int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                    uint32_t box_inner, uint32_t box_outer) {
+  std::call_once(g_encode_once, resolve_encode);
+  if (g_encode == nullptr) { pa_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return PA_ERR_CUDA; }
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15)) { pa_set_error("TMA needs 16-byte aligned base and pitch"); return PA_ERR_ARG; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { pa_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return PA_ERR_CUDA; }
+  return PA_OK;
+}
+
+extern "C" int pa_gemm_tf32(const pa_gemm_args* a, void* stream) {
+  PA_CHECK_ARG(a != nullptr && a->M > 0 && a->N > 0 && a->K > 0);
+  PA_CHECK_ARG(a->lda % 4 == 0 && a->ldb % 4 == 0);
+  PA_CHECK_ARG(!(a->batch > 1 && (a->a_mn || a->split_k > 1)));
+  PA_CHECK_ARG(!(a->split_k > 1 && !a->accumulate));
+  PA_CHECK_ARG(!(a->accumulate && (a->bias != nullptr || a->relu || a->p_drop > 0.f)));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool wide = a->N > 128 && (a->N % 256 == 0 || a->N > 1024);
+  if (!a->a_mn && !a->b_mn) return wide ? launch<256, false, false>(*a, st) : launch<128, false, false>(*a, st);
+  if (a->a_mn && a->b_mn) return launch<128, true, true>(*a, st);
+  if (!a->a_mn && a->b_mn) return (a->N % 256 == 0) ? launch<256, false, true>(*a, st) : launch<128, false, true>(*a, st);
+  pa_set_error("pa_gemm_tf32: mixed operand majors are not built (a_mn=%d b_mn=%d)", a->a_mn, a->b_mn);
+  return PA_ERR_UNSUPPORTED;
+}

@@ -143,17 +143,16 @@ class PlankModel(nn.Module):
                                      self.query_coord_embedding.weight, self.query_pos_embedding.weight)
 
     def _ffn(self, layer, x):
-        h = F.linear(x, layer.linear1.weight, layer.linear1.bias)
-        h = ops.ReluDropout.apply(h, self._p())
-        return F.linear(h, layer.linear2.weight, layer.linear2.bias)
+        h = ops.linear(x, layer.linear1.weight, layer.linear1.bias, relu=True, p_drop=self._p())
+        return ops.linear(h, layer.linear2.weight, layer.linear2.bias)
 
     def _encode(self, x, in_kpm):
         p, H = self._p(), self.num_head
         for layer in self.encoder.layers:
             sa = layer.self_attn
-            qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+            qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
             a = ops.SelfAttention.apply(qkv, in_kpm, H, False, p, self._impl())
-            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias)
             x = ops.AddLayerNorm.apply(x, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
             x = ops.AddLayerNorm.apply(x, self._ffn(layer, x), layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
         if self.encoder.norm is not None:
@@ -164,21 +163,21 @@ class PlankModel(nn.Module):
         p, H, d = self._p(), self.num_head, self.num_model
         for layer in self.decoder.layers:
             sa, ca = layer.self_attn, layer.multihead_attn
-            qkv = F.linear(y, sa.in_proj_weight, sa.in_proj_bias)
+            qkv = ops.linear(y, sa.in_proj_weight, sa.in_proj_bias)
             a = ops.SelfAttention.apply(qkv, out_kpm, H, True, p, self._impl())
-            a = F.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias)
             y = ops.AddLayerNorm.apply(y, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
-            q = F.linear(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
-            kv = F.linear(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:])
+            q = ops.linear(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
+            kv = ops.linear(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:])
             a = ops.CrossAttention.apply(q, kv, in_kpm, H, p, self._impl())
-            a = F.linear(a, ca.out_proj.weight, ca.out_proj.bias)
+            a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias)
             y = ops.AddLayerNorm.apply(y, a, layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
             y = ops.AddLayerNorm.apply(y, self._ffn(layer, y), layer.norm3.weight, layer.norm3.bias, self.layer_eps, p)
         return ops.AddLayerNorm.apply(y, None, self.decoder.norm.weight, self.decoder.norm.bias, 1e-5, 0.0)
 
     def _heads(self, h):
-        lv = F.linear(h, self.vocab_head.weight, self.vocab_head.bias)
-        pf = F.linear(h, self.pointer_head.weight, self.pointer_head.bias)
+        lv = ops.linear(h, self.vocab_head.weight, self.vocab_head.bias)
+        pf = ops.linear(h, self.pointer_head.weight, self.pointer_head.bias)
         lp = torch.bmm(pf, h.transpose(1, 2))                      # raw scores; 1/d applied in the kernel
         sw = F.linear(h, self.switch_head.weight, self.switch_head.bias).squeeze(-1)
         return lv, lp, sw

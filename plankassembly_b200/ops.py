@@ -13,7 +13,9 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from ._lib import AttnBwdArgs, AttnFwdArgs, call
+import os
+
+from ._lib import AttnBwdArgs, AttnFwdArgs, GemmArgs, call
 
 ATTN_IMPL = {'simt': 0, 'tc': 1}
 
@@ -121,7 +123,7 @@ class AddLayerNorm(Function):
         d = x.shape[-1]
         rows = x.numel() // d
         y = torch.empty_like(x)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad or (a is not None and a.requires_grad))
+        need_grad = any(ctx.needs_input_grad)
         s = torch.empty_like(x) if (need_grad and a is not None) else None
         stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
         seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
@@ -202,7 +204,7 @@ class SelfAttention(Function):
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
         base = qkv.data_ptr()
         o, lse = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
-                           impl, torch.is_grad_enabled() and qkv.requires_grad, qkv.device)
+                           impl, any(ctx.needs_input_grad), qkv.device)
         ctx.save_for_backward(qkv, o, lse, kpm)
         ctx.cfg = (H, causal, p_drop, seed, off, impl)
         return o
@@ -232,7 +234,7 @@ class CrossAttention(Function):
         Lk = kv.shape[1]
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
         kb = kv.data_ptr()
-        need = torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad)
+        need = any(ctx.needs_input_grad)
         o, lse = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
                            impl, need, q.device)
         ctx.save_for_backward(q, kv, o, lse, kpm)
@@ -251,6 +253,83 @@ class CrossAttention(Function):
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
                   d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, 0)
         return dq, dkv, None, None, None, None
+
+
+def gemm_tf32(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, bias=None, relu=False, p_drop=0.0, seed=0, off=0,
+              alpha=1.0, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, split_k=1, accumulate=False):
+    """C = alpha * op(A) op(B)^T (+bias)(relu)(dropout) on the tcgen05 tensor cores (TF32 in, FP32 acc)."""
+    g = GemmArgs(a.data_ptr(), lda, int(a_mn), b.data_ptr(), ldb, int(b_mn), c.data_ptr(), ldc, _ptr(bias), int(relu), p_drop,
+                 seed, off, alpha, M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, split_k, int(accumulate))
+    call('pa_gemm_tf32', C.byref(g), _stream())
+    return c
+
+
+def _split_k(tiles, k_blocks):
+    """Split the contraction of a weight-gradient GEMM so ~one wave of CTAs covers the 148 SMs."""
+    sk = max(1, 148 // max(1, tiles))
+    return max(1, min(sk, k_blocks // 8 if k_blocks >= 8 else 1))
+
+
+class Linear(Function):
+    """y = x W^T + b (optionally relu + dropout fused in the GEMM epilogue), TF32 tensor cores.
+    Backward: dx = dy W  (B operand MN-major: W as stored), dW = dy^T x (both operands MN-major,
+    split-K over the tokens with fp32 RED), db = column sums of dy."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, p_drop):
+        _require_cuda(x, W)
+        K, N = W.shape[1], W.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        assert W.stride(1) == 1
+        M = x2.shape[0]
+        y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        seed, off = RNG.next() if p_drop > 0 else (0, 0)
+        gemm_tf32(x2, W, y, M, N, K, lda=K, ldb=W.stride(0), ldc=N, bias=b, relu=relu, p_drop=p_drop, seed=seed, off=off)
+        ctx.save_for_backward(x2, W, y if (relu or p_drop > 0) else None)
+        ctx.cfg = (relu, p_drop, b is not None, x.shape)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, W, y = ctx.saved_tensors
+        relu, p_drop, has_b, xshape = ctx.cfg
+        N, K = W.shape
+        M = x2.shape[0]
+        dy2 = dy.reshape(M, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if y is not None:
+            dy2 = dy2.clone()
+            call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, _stream())
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+            gemm_tf32(dy2, W, dx, M, K, N, lda=N, ldb=W.stride(0), ldc=K, b_mn=True)
+            dx = dx.view(xshape)
+        if ctx.needs_input_grad[1]:
+            dW = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
+            tiles = ((N + 127) // 128) * ((K + 127) // 128)
+            gemm_tf32(dy2, x2, dW, N, K, M, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True,
+                      split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
+        if has_b and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dW, db, None, None
+
+
+GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'cublas')
+
+
+def linear(x, W, b, relu=False, p_drop=0.0):
+    """Dense projection used by the model: our tcgen05 GEMM ('tc') or cuBLAS fp32 ('cublas')."""
+    if os.environ.get('PLANK_B200_GEMM', GEMM_IMPL) == 'tc':
+        return Linear.apply(x, W, b, relu, p_drop)
+    y = torch.nn.functional.linear(x, W, b)
+    if relu:
+        y = ReluDropout.apply(y, p_drop)
+    return y
 
 
 class DistLoss(Function):

@@ -1,0 +1,110 @@
+"""tcgen05 TF32 GEMM (pa_gemm_tf32) against fp64 math.  Two references: exact fp64 (tolerance =
+TF32 operand rounding, 2^-11 relative per operand) and fp64 on TF32-truncated operands (tight)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _util import rel_err  # noqa: E402
+
+
+def tf32_trunc(x):
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def check(out, a64, b64, a_t, b_t, tag, alpha=1.0):
+    ref = alpha * (a64 @ b64.T)
+    ref_t = alpha * (a_t.double() @ b_t.double().T)
+    e, et = rel_err(out.cpu(), ref), rel_err(out.cpu(), ref_t)
+    print(f'{tag}: rel err vs fp64 {e:.2e}, vs tf32-truncated operands {et:.2e}')
+    assert e < 2e-3, tag
+    return e, et
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 128, 128), (1196, 1536, 512), (4096, 514, 512), (300, 1024, 256), (128, 512, 1024), (64, 1536, 512)])
+def test_gemm_kmajor_bias(M, N, K):
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    c = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm_tf32(a.cuda(), w.cuda(), c, M, N, K, lda=K, ldb=K, ldc=N, bias=bias.cuda())
+    out = c.cpu() - bias
+    check(out, a.double(), w.double(), tf32_trunc(a), tf32_trunc(w), f'TN {M}x{N}x{K}')
+
+
+def test_gemm_relu_dropout_epilogue():
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    M, N, K, p = 512, 1024, 512, 0.2
+    a, w, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    c = torch.empty(M, N, device='cuda')
+    ops.gemm_tf32(a.cuda(), w.cuda(), c, M, N, K, lda=K, ldb=K, ldc=N, bias=bias.cuda(), relu=True)
+    ref = torch.relu(a.double() @ w.double().T + bias)
+    assert rel_err(c.cpu(), ref) < 2e-3
+    c2 = torch.empty(M, N, device='cuda')
+    ops.gemm_tf32(a.cuda(), w.cuda(), c2, M, N, K, lda=K, ldb=K, ldc=N, bias=bias.cuda(), relu=True, p_drop=p, seed=7, off=3)
+    keep = c2 > 0
+    pos = c > 0
+    assert abs(keep[pos].float().mean().item() - (1 - p)) < 1e-2
+    assert torch.allclose(c2[keep], c[keep] / (1 - p), rtol=1e-6)
+    # the elementwise kernel must regenerate the very same mask (shared Philox indexing)
+    z = c.clone()
+    from plankassembly_b200._lib import call
+    call('pa_relu_dropout_fwd', z.data_ptr(), z.numel(), p, 7, 3, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(z > 0, keep)
+
+
+@pytest.mark.parametrize('M,N,K', [(1196, 512, 1536), (4096, 256, 1024), (256, 1024, 512)])
+def test_gemm_dx_form(M, N, K):
+    """dx = dy @ W with W [K(contract), N(out)] as stored: A K-major, B MN-major."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    dy = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / K ** 0.5
+    c = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm_tf32(dy.cuda(), w.cuda(), c, M, N, K, lda=K, ldb=N, ldc=N, b_mn=True)
+    check(c, dy.double(), w.double().T, tf32_trunc(dy), tf32_trunc(w).T, f'dX {M}x{N}x{K}')
+
+
+@pytest.mark.parametrize('Mtok,N,K,split', [(1196, 512, 256, 1), (4096, 1536, 512, 3), (2048, 514, 512, 2)])
+def test_gemm_dw_form(Mtok, N, K, split):
+    """dW[N,K] = dy^T x: both operands MN-major (stored [tokens, features]), split-K + RED."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    dy = torch.randn(Mtok, N, generator=g)
+    x = torch.randn(Mtok, K, generator=g)
+    c = torch.zeros(N, K, device='cuda')
+    ops.gemm_tf32(dy.cuda(), x.cuda(), c, N, K, Mtok, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True, split_k=split, accumulate=True)
+    check(c, dy.double().T, x.double().T, tf32_trunc(dy).T, tf32_trunc(x).T, f'dW {N}x{K}x{Mtok}')
+
+
+def test_gemm_batched_pointer_scores():
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for B, T, d in [(3, 256, 512), (4, 64, 128), (2, 128, 512)]:
+        pf, h = torch.randn(B, T, d, generator=g), torch.randn(B, T, d, generator=g)
+        c = torch.full((B, T, T), float('nan'), device='cuda')
+        ops.gemm_tf32(pf.cuda(), h.cuda(), c, T, T, d, lda=d, ldb=d, ldc=T, batch=B, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T)
+        ref = pf.double() @ h.double().transpose(1, 2)
+        assert rel_err(c.cpu(), ref) < 2e-3, (B, T, d)
+
+
+def test_linear_autograd_matches_torch():
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, L, K, N = 4, 299, 512, 1536
+    x = torch.randn(B, L, K, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.linear(x, w, b)
+    gy = torch.randn(B, L, N, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    cx, cw, cb = (t.detach().float().cuda().requires_grad_(True) for t in (x, w, b))
+    out = ops.Linear.apply(cx, cw, cb, False, 0.0)
+    assert rel_err(out.cpu(), ref.detach()) < 2e-3
+    (out * gy.float().cuda()).sum().backward()
+    assert rel_err(cx.grad.cpu(), x.grad) < 2e-3
+    assert rel_err(cw.grad.cpu(), w.grad) < 2e-3
+    assert rel_err(cb.grad.cpu(), b.grad) < 1e-5

@@ -38,10 +38,13 @@ def test_train_step_matches_reference(name):
     assert rel_err(out['memory'][0, :nv].cpu(), g['memory0_valid']) < TOL
     out['loss'].backward()
     grads = dict(m.named_parameters())
+    # per-parameter gradient norms: 1e-3 relative, with an absolute floor of 1e-4 of the whole-model
+    # gradient norm (some gradients, e.g. the key bias, are mathematically ~0 and hold rounding noise only)
+    floor = 1e-4 * float(np.sqrt((g['grad_norms'] ** 2).sum()))
     for n, norm in zip(g['grad_names'], g['grad_norms']):
         gr = grads[str(n)].grad
         assert gr is not None, n
-        assert abs(gr.double().norm().item() - norm) <= TOL * norm + 1e-9, (n, gr.double().norm().item(), norm)
+        assert abs(gr.double().norm().item() - norm) <= TOL * norm + floor, (n, gr.double().norm().item(), norm)
     for k in g:
         if k.startswith('grad:'):
             assert rel_err(grads[k[5:]].grad.cpu(), g[k]) < TOL, k
