@@ -132,10 +132,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tc::tc_fence_after();
           const uint32_t sa = tc::smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          // K-major: LBO unused, SBO = 1024 (8 rows x 128 B).  MN-major: LBO = one 32-wide MN block
-          // (BK rows x 128 B), SBO = 1024 (8 K rows).
-          const uint64_t da = tc::make_smem_desc(sa, A_MN ? BK * 128 : 16, 1024);
-          const uint64_t db = tc::make_smem_desc(sb, B_MN ? BK * 128 : 16, 1024);
+          // K-major: LBO unused, SBO = 1024 (8 rows x 128 B).  MN-major (tf32 => 128B_BASE32B): LBO = one
+          // 32-wide MN block (BK rows x 128 B), SBO = 512 (4 K rows); one MMA (K=8) spans two K groups.
+          const uint64_t da = A_MN ? tc::make_smem_desc(sa, BK * 128, 512, tc::kLayoutSw128Base32) : tc::make_smem_desc(sa, 16, 1024);
+          const uint64_t db = B_MN ? tc::make_smem_desc(sb, BK * 128, 512, tc::kLayoutSw128Base32) : tc::make_smem_desc(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t dak = tc::desc_advance(da, A_MN ? k * 1024 : k * UK * 4);
@@ -232,10 +232,10 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
-  else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 4, 32, BK);
+  else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 4, 32, BK, true);
   if (rc) return rc;
   if (!B_MN) rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.N), (uint64_t)a.ldb * 4, BK, BN);
-  else rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.N, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.K), (uint64_t)a.ldb * 4, 32, BK);
+  else rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.N, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.K), (uint64_t)a.ldb * 4, 32, BK, true);
   if (rc) return rc;
   GemmParams p{};
   p.c = a.c; p.ldc = a.ldc; p.c_batch_stride = a.c_batch_stride; p.bias = a.bias;
@@ -260,7 +260,7 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
 }  // namespace
 
 int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                    uint32_t box_inner, uint32_t box_outer) {
+                    uint32_t box_inner, uint32_t box_outer, bool atom32) {
   std::call_once(g_encode_once, resolve_encode);
   if (g_encode == nullptr) { pa_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return PA_ERR_CUDA; }
   if (((uintptr_t)base & 15) || (pitch_bytes & 15)) { pa_set_error("TMA needs 16-byte aligned base and pitch"); return PA_ERR_ARG; }
@@ -269,7 +269,8 @@ int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { pa_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return PA_ERR_CUDA; }
   return PA_OK;

@@ -125,13 +125,19 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 //              LBO unused (1).  Advancing K by one MMA (8 tf32 = 32 B) adds 32 B to the start address.
 //   MN-major : each K row is a 128-B line of 32 consecutive MN elements; 8 K rows = one 1024-B atom;
 //              LBO = bytes between 32-element MN blocks, SBO = bytes between 8-row K groups.
-__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major, 32-bit elements (tf32): the ONLY legal form is SWIZZLE_128B_BASE32B (layout_type 1): 32-byte
+//              chunks swizzled within the 128-B line over a 4-row (512 B) atom -- TMA mode
+//              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  SBO = bytes between 4-row K groups (512), LBO = bytes
+//              between 32-element MN blocks.  (With layout_type 2 the MMA silently returns zeros.)
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                            uint32_t layout_type = kLayoutSw128) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
@@ -145,5 +151,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 }  // namespace tc
 
 // Host: 2-D fp32 tensor map with 128-byte swizzle.  dims/box are {inner, outer}; pitch in bytes.
+// atom32 = true selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32 operands).
 int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                    uint32_t box_inner, uint32_t box_outer);
+                    uint32_t box_inner, uint32_t box_outer, bool atom32 = false);

@@ -304,22 +304,25 @@ class Linear(Function):
         if y is not None:
             dy2 = dy2.clone()
             call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, _stream())
-        dx = dW = db = None
+        db = dy2.sum(0) if (has_b and ctx.needs_input_grad[2]) else None
+        ldn = N
+        if N % 4:                         # TMA needs a 16-byte row pitch (vocab head: N = 514)
+            ldn = (N + 3) // 4 * 4
+            dy2 = torch.nn.functional.pad(dy2, (0, ldn - N))
+        dx = dW = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
-            gemm_tf32(dy2, W, dx, M, K, N, lda=N, ldb=W.stride(0), ldc=K, b_mn=True)
+            gemm_tf32(dy2, W, dx, M, K, N, lda=ldn, ldb=W.stride(0), ldc=K, b_mn=True)
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1]:
             dW = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
             tiles = ((N + 127) // 128) * ((K + 127) // 128)
-            gemm_tf32(dy2, x2, dW, N, K, M, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True,
+            gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
-        if has_b and ctx.needs_input_grad[2]:
-            db = dy2.sum(0)
         return dx, dW, db, None, None
 
 
-GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'cublas')
+GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 
 
 def linear(x, W, b, relu=False, p_drop=0.0):

@@ -76,7 +76,9 @@ def test_gemm_dw_form(Mtok, N, K, split):
     dy = torch.randn(Mtok, N, generator=g)
     x = torch.randn(Mtok, K, generator=g)
     c = torch.zeros(N, K, device='cuda')
-    ops.gemm_tf32(dy.cuda(), x.cuda(), c, N, K, Mtok, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True, split_k=split, accumulate=True)
+    ldn = (N + 3) // 4 * 4                   # TMA wants a 16-byte pitch: pad the row, keep the logical N
+    dyp = torch.nn.functional.pad(dy, (0, ldn - N)).cuda()
+    ops.gemm_tf32(dyp, x.cuda(), c, N, K, Mtok, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True, split_k=split, accumulate=True)
     check(c, dy.double().T, x.double().T, tf32_trunc(dy).T, tf32_trunc(x).T, f'dW {N}x{K}x{Mtok}')
 
 
@@ -108,3 +110,22 @@ def test_linear_autograd_matches_torch():
     assert rel_err(cx.grad.cpu(), x.grad) < 2e-3
     assert rel_err(cw.grad.cpu(), w.grad) < 2e-3
     assert rel_err(cb.grad.cpu(), b.grad) < 1e-5
+
+
+def test_linear_vocab_head_shape():
+    """N = 514 (not a multiple of 4): scalar-store epilogue + padded dy in backward."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    M, K, N = 1024, 512, 514
+    x = torch.randn(M, K, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.linear(x, w, b)
+    gy = torch.randn(M, N, generator=g, dtype=torch.float64)
+    (ref * gy).sum().backward()
+    cx, cw, cb = (t.detach().float().cuda().requires_grad_(True) for t in (x, w, b))
+    out = ops.Linear.apply(cx, cw, cb, False, 0.0)
+    assert rel_err(out.cpu(), ref.detach()) < 2e-3
+    (out * gy.float().cuda()).sum().backward()
+    assert rel_err(cx.grad.cpu(), x.grad) < 2e-3
+    assert rel_err(cw.grad.cpu(), w.grad) < 2e-3
