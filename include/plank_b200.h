@@ -35,16 +35,20 @@ int pa_device_ok(void);
  * gathers + 4 adds).  out[n,:] = sum_k tables[k][ids[k][n], :].  bwd accumulates (+=) into
  * dtables[k] (the value table is shared with the decoder side, models.py:120). */
 int pa_embed_input_fwd(const int64_t* const* ids_host, const float* const* tables_host, int n_tables,
-                       int64_t n_tokens, int d, float* out, void* stream);
+                       int64_t n_tokens, int d, float* out, float* out_tf32, void* stream);
 int pa_embed_input_bwd(const float* dout, const int64_t* const* ids_host, float* const* dtables_host,
                        const int* table_rows_host, int n_tables, int64_t n_tokens, int d, void* stream);
 
 /* ---- K2: decoder-input embedding, shifted right by one with a zero row (models.py:114-138).
  * out[b,0,:] = 0; out[b,t,:] = e_val[value[b*ld+t-1]] + e_coord[(t-1)%dof] + e_pos[(t-1)/dof]. */
 int pa_embed_output_fwd(const int64_t* value, int64_t ld, int B, int T, int dof, const float* e_val,
-                        const float* e_coord, const float* e_pos, int d, float* out, void* stream);
+                        const float* e_coord, const float* e_pos, int d, float* out, float* out_tf32, void* stream);
 int pa_embed_output_bwd(const float* dout, const int64_t* value, int64_t ld, int B, int T, int dof,
                         float* d_val, float* d_coord, float* d_pos, int d, void* stream);
+
+/* TF32 policy: tcgen05 kind::tf32 truncates raw fp32 operands (a systematic ~2^-11 bias per product, which
+ * breaks the 1e-3 parity bar), so every tensor that feeds a tensor-core operand is ROUNDED TO NEAREST TF32
+ * by the kernel that produces it: `*_tf32` outputs are rounded copies, `round_*` flags round in place. */
 
 /* ---- K6/K7: y = LayerNorm_eps(x + dropout_p(a)) -- the post-norm residual blocks of
  * torch nn/modules/transformer.py (encoder :952-956, decoder :1144-1153) as configured by
@@ -52,18 +56,20 @@ int pa_embed_output_bwd(const float* dout, const int64_t* value, int64_t ld, int
  * (final norms).  s receives the pre-norm sum (saved for bwd; may alias nothing, may be NULL
  * in inference); stats = [rows,2] (mean, rstd), may be NULL in inference. */
 int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
-                  float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* s,
+                  float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
                   float* stats, void* stream);
 /* dx = grad wrt x (and wrt s); da = dropout-masked copy (may be NULL); dgamma/dbeta are
- * accumulated (+=).  partial = workspace of pa_add_ln_bwd_workspace(rows,d) bytes. */
+ * accumulated (+=).  dy2 (may be NULL) is a second incoming gradient added to dy (the TF32 copy's).  partial = workspace of pa_add_ln_bwd_workspace(rows,d) bytes. */
 size_t pa_add_ln_bwd_workspace(int64_t rows, int d);
-int pa_add_ln_bwd(const float* dy, const float* s, const float* stats, const float* gamma, float p_drop,
-                  uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, float* dgamma,
-                  float* dbeta, void* partial, void* stream);
+int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma,
+                  float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da,
+                  int round_da, float* dgamma, float* dbeta, void* partial, void* stream);
 
 /* ---- FFN activation: z <- dropout_p(relu(z)) in place (transformer.py _ff_block). */
 int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t seed, uint64_t offset, void* stream);
-int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, void* stream);
+int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, int round_tf32, void* stream);
+/* dst = round-to-nearest-TF32(src): shadow copies of the weights for the tensor-core path. */
+int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 /* x <- dropout_p(x) in place (sub-block output dropouts are fused into pa_add_ln_*). */
 
 /* ---- K3/K4/K5: multi-head attention core (torch nn/functional.py multi_head_attention_forward
@@ -83,6 +89,7 @@ typedef struct {
   float scale;
   float p_drop; uint64_t seed, offset;
   int impl;
+  int round_out;               /* write O rounded to TF32 (it feeds a tensor-core GEMM) */
 } pa_attn_fwd_args;
 int pa_attn_fwd(const pa_attn_fwd_args* args, void* stream);
 
@@ -100,6 +107,7 @@ typedef struct {
   float scale;
   float p_drop; uint64_t seed, offset;
   int impl;
+  int round_out;               /* write dq/dk/dv rounded to TF32 */
 } pa_attn_bwd_args;
 int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
 
@@ -120,6 +128,7 @@ typedef struct {
   int M, N, K;
   int batch; int64_t a_batch_rows, b_batch_rows, c_batch_stride;
   int split_k; int accumulate;
+  int round_out;               /* write C rounded to TF32 (when C only feeds tensor-core operands) */
 } pa_gemm_args;
 int pa_gemm_tf32(const pa_gemm_args* args, void* stream);
 
@@ -134,7 +143,7 @@ int pa_dist_loss_fwd(const float* lv, const float* lp, const float* sw, const in
 /* gout: device scalar dL/dloss.  Writes dlv [N,V], dlp [N,T] (wrt the RAW scores), dsw [N]. */
 int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const int64_t* label,
                      const float* rowstat, const float* accum, const float* gout, int B, int T, int V,
-                     int pad, float inv_d, float* dlv, float* dlp, float* dsw, void* stream);
+                     int pad, float inv_d, float* dlv, float* dlp, float* dsw, int round_tf32, void* stream);
 /* Optional full distribution (parity tests only): dists [N, V+T] as models.py:186 builds it. */
 int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
                        float* dists, void* stream);

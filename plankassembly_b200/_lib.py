@@ -14,7 +14,7 @@ class AttnFwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i64), ('ldk', i64), ('ldv', i64),
                 ('o', vp), ('ldo', i64), ('lse', vp), ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
-                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32)]
+                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -23,14 +23,14 @@ class AttnBwdArgs(C.Structure):
                 ('dq', vp), ('dk', vp), ('dv', vp), ('lddq', i64), ('lddk', i64), ('lddv', i64),
                 ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
-                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32)]
+                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32)]
 
 
 class GemmArgs(C.Structure):
     _fields_ = [('a', vp), ('lda', i64), ('a_mn', i32), ('b', vp), ('ldb', i64), ('b_mn', i32),
                 ('c', vp), ('ldc', i64), ('bias', vp), ('relu', i32), ('p_drop', f32), ('seed', u64), ('offset', u64),
                 ('alpha', f32), ('M', i32), ('N', i32), ('K', i32), ('batch', i32),
-                ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32)]
+                ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32), ('round_out', i32)]
 
 
 # name -> (restype, argtypes); mirrors include/plank_b200.h one to one
@@ -38,20 +38,21 @@ SIGNATURES = {
     'pa_abi_version': (i32, []),
     'pa_last_error': (C.c_char_p, []),
     'pa_device_ok': (i32, []),
-    'pa_embed_input_fwd': (i32, [C.POINTER(vp), C.POINTER(vp), i32, i64, i32, vp, vp]),
+    'pa_embed_input_fwd': (i32, [C.POINTER(vp), C.POINTER(vp), i32, i64, i32, vp, vp, vp]),
     'pa_embed_input_bwd': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i32, i64, i32, vp]),
-    'pa_embed_output_fwd': (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    'pa_embed_output_fwd': (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     'pa_embed_output_bwd': (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp]),
-    'pa_add_ln_fwd': (i32, [vp, vp, vp, vp, f32, f32, u64, u64, i64, i32, vp, vp, vp, vp]),
+    'pa_add_ln_fwd': (i32, [vp, vp, vp, vp, f32, f32, u64, u64, i64, i32, vp, vp, vp, vp, vp]),
     'pa_add_ln_bwd_workspace': (sz, [i64, i32]),
-    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, vp, vp, vp, vp]),
+    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
     'pa_relu_dropout_fwd': (i32, [vp, i64, f32, u64, u64, vp]),
-    'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, vp]),
+    'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, i32, vp]),
+    'pa_round_tf32': (i32, [vp, vp, i64, vp]),
     'pa_attn_fwd': (i32, [C.POINTER(AttnFwdArgs), vp]),
     'pa_attn_bwd': (i32, [C.POINTER(AttnBwdArgs), vp]),
     'pa_gemm_tf32': (i32, [C.POINTER(GemmArgs), vp]),
     'pa_dist_loss_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
-    'pa_dist_loss_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+    'pa_dist_loss_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp]),
     'pa_dist_train_full': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
     'pa_decode_embed': (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     'pa_decode_attn': (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i32, i32, vp, i32, i32, i32, f32, vp, vp]),

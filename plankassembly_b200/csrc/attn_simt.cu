@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_simt_kernel(pa_attn_fwd_args A) {
     const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
     float* op = A.o + ((int64_t)b * A.Lq + qi) * A.ldo + h * DH + tx * W;
 #pragma unroll
-    for (int w = 0; w < W; ++w) op[w] = o[r][w] * inv;
+    for (int w = 0; w < W; ++w) op[w] = A.round_out ? tf32_rn(o[r][w] * inv) : o[r][w] * inv;
     if (A.lse != nullptr && tx == 0)
       A.lse[((int64_t)b * A.H + h) * A.Lq + qi] = l_run[r] > 0.f ? m_run[r] + __logf(l_run[r]) : -INFINITY;
   }
@@ -307,7 +307,10 @@ __global__ void __launch_bounds__(NT) attn_bwd_dkdv_simt_kernel(pa_attn_bwd_args
     float* pk = A.dk + ((int64_t)b * A.Lk + kj) * A.lddk + h * DH + tx * W;
     float* pv = A.dv + ((int64_t)b * A.Lk + kj) * A.lddv + h * DH + tx * W;
 #pragma unroll
-    for (int w = 0; w < W; ++w) { pk[w] = dk[r][w] * A.scale; pv[w] = dv[r][w]; }
+    for (int w = 0; w < W; ++w) {
+      float a = dk[r][w] * A.scale, c = dv[r][w];
+      pk[w] = A.round_out ? tf32_rn(a) : a; pv[w] = A.round_out ? tf32_rn(c) : c;
+    }
   }
 }
 
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_dq_simt_kernel(pa_attn_bwd_args A
     if (qi >= A.Lq) continue;
     float* p = A.dq + ((int64_t)b * A.Lq + qi) * A.lddq + h * DH + tx * W;
 #pragma unroll
-    for (int w = 0; w < W; ++w) p[w] = dq[r][w] * A.scale;
+    for (int w = 0; w < W; ++w) p[w] = A.round_out ? tf32_rn(dq[r][w] * A.scale) : dq[r][w] * A.scale;
   }
 }
 

@@ -36,6 +36,16 @@ void pa_set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// Round-to-nearest conversion to TF32 (10-bit mantissa, low 13 bits zero).  tcgen05 kind::tf32 reads raw
+// fp32 bits and TRUNCATES them, which biases every product by ~2^-11; operands that were rounded here
+// are already exactly representable, so the MMA sees unbiased values.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -12,7 +12,7 @@ struct EmbedTables {
   int n;
 };
 
-__global__ void __launch_bounds__(256) embed_input_fwd_kernel(EmbedTables T, int64_t n_tokens, int d4, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) embed_input_fwd_kernel(EmbedTables T, int64_t n_tokens, int d4, float4* __restrict__ out, float4* __restrict__ out_r) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tokens * d4) return;
   int64_t tok = idx / d4;
@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) embed_input_fwd_kernel(EmbedTables T, int
     }
   }
   out[idx] = acc;
+  if (out_r != nullptr) out_r[idx] = tf32_rn4(acc);
 }
 
 // Backward: one block owns a chunk of tokens; thread c owns float4 column c.  Large tables take
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(128) embed_input_bwd_kernel(EmbedTables T, int
 
 __global__ void __launch_bounds__(256) embed_output_fwd_kernel(const int64_t* __restrict__ value, int64_t ld, int B, int Tn, int dof,
                                                                   const float4* __restrict__ e_val, const float4* __restrict__ e_coord,
-                                                                  const float4* __restrict__ e_pos, int d4, float4* __restrict__ out) {
+                                                                  const float4* __restrict__ e_pos, int d4, float4* __restrict__ out, float4* __restrict__ out_r) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * Tn * d4) return;
   int c = (int)(idx % d4);
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) embed_output_fwd_kernel(const int64_t* __
     acc.x = (v.x + q.x) + p.x; acc.y = (v.y + q.y) + p.y; acc.z = (v.z + q.z) + p.z; acc.w = (v.w + q.w) + p.w;
   }
   out[idx] = acc;
+  if (out_r != nullptr) out_r[idx] = tf32_rn4(acc);
 }
 
 // Backward: block = one decoder position t (> 0) x a slice of the batch.  coord/pos rows depend
@@ -131,14 +133,14 @@ __global__ void __launch_bounds__(128) decode_embed_kernel(const int64_t* __rest
 }
 
 extern "C" int pa_embed_input_fwd(const int64_t* const* ids_host, const float* const* tables_host, int n_tables,
-                                  int64_t n_tokens, int d, float* out, void* stream) {
+                                  int64_t n_tokens, int d, float* out, float* out_tf32, void* stream) {
   PA_CHECK_ARG(n_tables >= 1 && n_tables <= PA_MAX_TABLES && d % 4 == 0 && n_tokens >= 0);
   if (n_tokens == 0) return PA_OK;
   EmbedTables T{};
   T.n = n_tables;
   for (int k = 0; k < n_tables; ++k) { T.ids[k] = ids_host[k]; T.tab[k] = tables_host[k]; }
   int64_t total = n_tokens * (d / 4);
-  embed_input_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n_tokens, d / 4, (float4*)out);
+  embed_input_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n_tokens, d / 4, (float4*)out, (float4*)out_tf32);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
@@ -156,11 +158,11 @@ extern "C" int pa_embed_input_bwd(const float* dout, const int64_t* const* ids_h
 }
 
 extern "C" int pa_embed_output_fwd(const int64_t* value, int64_t ld, int B, int T, int dof, const float* e_val,
-                                   const float* e_coord, const float* e_pos, int d, float* out, void* stream) {
+                                   const float* e_coord, const float* e_pos, int d, float* out, float* out_tf32, void* stream) {
   PA_CHECK_ARG(B > 0 && T > 0 && dof > 0 && d % 4 == 0);
   int64_t total = (int64_t)B * T * (d / 4);
   embed_output_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      value, ld, B, T, dof, (const float4*)e_val, (const float4*)e_coord, (const float4*)e_pos, d / 4, (float4*)out);
+      value, ld, B, T, dof, (const float4*)e_val, (const float4*)e_coord, (const float4*)e_pos, d / 4, (float4*)out, (float4*)out_tf32);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

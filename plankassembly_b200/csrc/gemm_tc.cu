@@ -33,6 +33,7 @@ struct GemmParams {
   int split_k; int accumulate;
   int relu; float p_drop; uint64_t seed, offset;
   float alpha;
+  int round_out;
   int m_tiles, n_tiles;
 };
 
@@ -188,6 +189,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               v[0] = rn.x >= thr ? v[0] * ks : 0.f; v[1] = rn.y >= thr ? v[1] * ks : 0.f;
               v[2] = rn.z >= thr ? v[2] * ks : 0.f; v[3] = rn.w >= thr ? v[3] * ks : 0.f;
             }
+            if (p.round_out) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = tf32_rn(v[e]);
+            }
             if (col + 3 < p.N && ((p.ldc & 3) == 0)) {
               float4 o = make_float4(v[0], v[1], v[2], v[3]);
               if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + col), o);
@@ -242,7 +247,7 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch < 1 ? 1 : a.batch;
   p.a_batch_rows = (int)a.a_batch_rows; p.b_batch_rows = (int)a.b_batch_rows;
   p.split_k = a.split_k < 1 ? 1 : a.split_k; p.accumulate = a.accumulate;
-  p.relu = a.relu; p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset; p.alpha = a.alpha;
+  p.relu = a.relu; p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset; p.alpha = a.alpha; p.round_out = a.round_out;
   p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static bool attr_done = false;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) dist_loss_bwd_kernel(const
                                                                              const float4* __restrict__ rowstat, const float* __restrict__ accum,
                                                                              const float* __restrict__ gout, int N, int T, int V, int pad,
                                                                              float inv_d, float* __restrict__ dlv, float* __restrict__ dlp,
-                                                                             float* __restrict__ dsw) {
+                                                                             float* __restrict__ dsw, int rnd) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * kRowsPerBlock + warp;
   if (n >= N) return;
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) dist_loss_bwd_kernel(const
   if (lab < V) {
     for (int c = lane; c < V; c += 32) {
       float p = __expf(__ldg(lv_row + c) - st.x);
-      dlv_row[c] = scale * (p - (c == lab ? 1.f : 0.f));
+      float gv = scale * (p - (c == lab ? 1.f : 0.f));
+      dlv_row[c] = rnd ? tf32_rn(gv) : gv;
     }
     for (int j = lane; j < T; j += 32) dlp_row[j] = 0.f;
     dpi = (1.f - pi) > kEps ? scale / (1.f - pi) : 0.f;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) dist_loss_bwd_kernel(const
     for (int j = lane; j < T; j += 32) {
       float g = 0.f;
       if (j < i) g = scale * (__expf(__ldg(lp_row + j) * inv_d - st.y) - (j == jl ? 1.f : 0.f)) * inv_d;
-      dlp_row[j] = g;
+      dlp_row[j] = rnd ? tf32_rn(g) : g;
     }
     dpi = pi > kEps ? -scale / pi : 0.f;
   }
@@ -271,11 +272,11 @@ extern "C" int pa_dist_loss_fwd(const float* lv, const float* lp, const float* s
 
 extern "C" int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const int64_t* label,
                                 const float* rowstat, const float* accum, const float* gout, int B, int T, int V,
-                                int pad, float inv_d, float* dlv, float* dlp, float* dsw, void* stream) {
+                                int pad, float inv_d, float* dlv, float* dlp, float* dsw, int round_tf32, void* stream) {
   PA_CHECK_ARG(B > 0 && T > 0 && V > 0);
   int N = B * T;
   dist_loss_bwd_kernel<<<(N + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      lv, lp, sw, label, (const float4*)rowstat, accum, gout, N, T, V, pad, inv_d, dlv, dlp, dsw);
+      lv, lp, sw, label, (const float4*)rowstat, accum, gout, N, T, V, pad, inv_d, dlv, dlp, dsw, round_tf32);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

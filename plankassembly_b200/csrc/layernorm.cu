@@ -14,7 +14,7 @@ template <int NV>  // float4 per lane; d = NV*128
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a,
                                                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float eps, float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
-                                                                     float4* __restrict__ y, float4* __restrict__ s_out, float2* __restrict__ stats) {
+                                                                     float4* __restrict__ y, float4* __restrict__ y_r, float4* __restrict__ s_out, float2* __restrict__ stats) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32;
   const float inv_d = 1.f / (float)(NV * 128);
@@ -58,16 +58,17 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
       y[row * d4 + c] = o;
+      if (y_r != nullptr) y_r[row * d4 + c] = tf32_rn4(o);
     }
     if (stats != nullptr && lane == 0) stats[row] = make_float2(mean, rstd);
   }
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ s,
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
                                                                      const float2* __restrict__ stats, const float4* __restrict__ gamma,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
-                                                                     float4* __restrict__ dx, float4* __restrict__ da, float* __restrict__ partial) {
+                                                                     float4* __restrict__ dx, float4* __restrict__ da, int round_da, float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32, d = NV * 128;
   const float inv_d = 1.f / (float)d;
@@ -84,6 +85,10 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
     for (int i = 0; i < NV; ++i) {
       int c = lane + i * 32;
       float4 dyv = __ldg(dy + row * d4 + c), sv = __ldg(s + row * d4 + c), gm = __ldg(gamma + c);
+      if (dy2 != nullptr) {
+        float4 e = __ldg(dy2 + row * d4 + c);
+        dyv.x += e.x; dyv.y += e.y; dyv.z += e.z; dyv.w += e.w;
+      }
       xh[i].x = (sv.x - st.x) * st.y; xh[i].y = (sv.y - st.x) * st.y; xh[i].z = (sv.z - st.x) * st.y; xh[i].w = (sv.w - st.x) * st.y;
       g[i].x = dyv.x * gm.x; g[i].y = dyv.y * gm.y; g[i].z = dyv.z * gm.z; g[i].w = dyv.w * gm.w;
       dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
           o.z = r.z >= thr ? o.z * keep_scale : 0.f;
           o.w = r.w >= thr ? o.w * keep_scale : 0.f;
         }
-        da[row * d4 + c] = o;
+        da[row * d4 + c] = round_da ? tf32_rn4(o) : o;
       }
     }
   }
@@ -149,7 +154,7 @@ static int ln_grid(int64_t rows) {
 extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 2 * d * sizeof(float); }
 
 extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
-                             float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* s,
+                             float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
                              float* stats, void* stream) {
   PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && p_drop >= 0.f && p_drop < 1.f);
   if (rows == 0) return PA_OK;
@@ -158,7 +163,7 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma,
 #define LAUNCH(NV)                                                                                                   \
   add_ln_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)x, (const float4*)a, (const float4*)gamma,     \
                                                          (const float4*)beta, eps, p_drop, seed, offset, rows,          \
-                                                         (float4*)y, (float4*)s, (float2*)stats)
+                                                         (float4*)y, (float4*)y_tf32, (float4*)s, (float2*)stats)
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -171,17 +176,17 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma,
   return PA_OK;
 }
 
-extern "C" int pa_add_ln_bwd(const float* dy, const float* s, const float* stats, const float* gamma, float p_drop,
-                             uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, float* dgamma,
+extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma, float p_drop,
+                             uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, int round_da, float* dgamma,
                              float* dbeta, void* partial, void* stream) {
   PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr);
   if (rows == 0) return PA_OK;
   int grid = ln_grid(rows);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
-  add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)s, (const float2*)stats,    \
+  add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)dy2, (const float4*)s, (const float2*)stats,    \
                                                          (const float4*)gamma, p_drop, seed, offset, rows, (float4*)dx, \
-                                                         (float4*)da, (float*)partial)
+                                                         (float4*)da, round_da, (float*)partial)
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -212,12 +217,12 @@ __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(float4* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float4* __restrict__ out, float4* __restrict__ g, int64_t n4, float ks) {
+__global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float4* __restrict__ out, float4* __restrict__ g, int64_t n4, float ks, int round_out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 o = __ldg(out + i), v = g[i];
     v.x = o.x > 0.f ? v.x * ks : 0.f; v.y = o.y > 0.f ? v.y * ks : 0.f;
     v.z = o.z > 0.f ? v.z * ks : 0.f; v.w = o.w > 0.f ? v.w * ks : 0.f;
-    g[i] = v;
+    g[i] = round_out ? tf32_rn4(v) : v;
   }
 }
 
@@ -231,12 +236,37 @@ extern "C" int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t s
   return PA_OK;
 }
 
-extern "C" int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, void* stream) {
+extern "C" int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, int round_tf32, void* stream) {
   PA_CHECK_ARG(n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f);
   if (n == 0) return PA_OK;
   int64_t n4 = n / 4;
   int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
-  relu_dropout_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, n4, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f);
+  relu_dropout_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, n4, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, round_tf32);
   PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+// dst = round-to-nearest TF32 of src (weight shadow copies for the tensor-core path)
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) dst[i] = tf32_rn4(__ldg(src + i));
+}
+__global__ void round_tf32_tail_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t begin, int64_t n) {
+  int64_t i = begin + threadIdx.x;
+  if (i < n) dst[i] = tf32_rn(src[i]);
+}
+
+extern "C" int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
+  PA_CHECK_ARG(n >= 0);
+  if (n == 0) return PA_OK;
+  int64_t n4 = n / 4;
+  if (n4 > 0) {
+    int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+    round_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, n4);
+    PA_CHECK_LAUNCH();
+  }
+  if (n4 * 4 < n) {
+    round_tf32_tail_kernel<<<1, 4, 0, (cudaStream_t)stream>>>(src, dst, n4 * 4, n);
+    PA_CHECK_LAUNCH();
+  }
   return PA_OK;
 }

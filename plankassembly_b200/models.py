@@ -8,8 +8,7 @@ and the reference's exact ``state_dict`` names/shapes, so its checkpoints load u
 
 What differs is underneath: no nn.Transformer.  Every op on the path is a hand-written sm_100a
 kernel behind the C ABI of include/plank_b200.h (embedding gather-sum, attention, residual+dropout
-+LayerNorm, pointer-head distribution/loss), the dense projections go through ``linear`` (see
-``gemm.py``), and eval mode runs a KV-cached greedy decoder (``decode.py``) instead of the
++LayerNorm, pointer-head distribution/loss, and the dense projections as a tcgen05 TF32 GEMM), and eval mode runs a KV-cached greedy decoder (``decode.py``) instead of the
 reference's O(T^3) recompute loop.  There is no CPU path: tensors must live on a B200.
 
 Reproduced quirks: the reference passes ``normalize_before`` into the
@@ -121,8 +120,15 @@ class PlankModel(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     # ------------------------------------------------------------------ building blocks
+    # Precision policy.  Training runs the dense contractions (projections, FFN, heads) on the tcgen05
+    # tensor cores in TF32 with FP32 accumulation; every tensor-core operand is rounded to nearest TF32
+    # by the kernel that produces it (tensors named *_r below), which keeps loss/logits inside the 1e-3
+    # parity bar.  Inference (eval_step) keeps everything in exact fp32 so greedy tokens stay bit-exact.
     def _p(self):
         return self.dropout if self.training else 0.0
+
+    def _tf32(self):
+        return self.training and ops.GEMM_IMPL == 'tc'
 
     def _impl(self):
         return ops.ATTN_IMPL[self.attn_impl]
@@ -131,53 +137,61 @@ class PlankModel(nn.Module):
     def _kpm(mask):
         return mask.contiguous().view(torch.uint8)
 
-    def _embed_input(self, inputs):
+    def _embed_input(self, inputs, want_r=False):
         keys = [k for k in inputs if 'mask' not in k]
         ids = [inputs[k] for k in keys]
         tables = [self.input_embeddings[k].weight for k in keys]
-        return ops.EmbedInput.apply(len(keys), *ids, *tables)
+        return ops.EmbedInput.apply(len(keys), want_r, *ids, *tables)
 
-    def _embed_output(self, output_value, T):
+    def _embed_output(self, output_value, T, want_r=False):
         """Embeds output_value[:, :T-1] behind a zero row -> [B,T,d] (ref models.py:114-138)."""
-        return ops.EmbedOutput.apply(output_value, T, self.num_output_dof, self.input_embeddings['input_value'].weight,
+        return ops.EmbedOutput.apply(output_value, T, self.num_output_dof, want_r, self.input_embeddings['input_value'].weight,
                                      self.query_coord_embedding.weight, self.query_pos_embedding.weight)
 
-    def _ffn(self, layer, x):
-        h = ops.linear(x, layer.linear1.weight, layer.linear1.bias, relu=True, p_drop=self._p())
-        return ops.linear(h, layer.linear2.weight, layer.linear2.bias)
+    def _add_ln(self, x, a, norm, eps, p, tf):
+        """-> (y, y_r): y_r is the TF32-rounded copy for the next GEMM (y itself in exact mode)."""
+        if tf:
+            return ops.AddLayerNorm.apply(x, a, norm.weight, norm.bias, eps, p, True, a is not None)
+        y = ops.AddLayerNorm.apply(x, a, norm.weight, norm.bias, eps, p, False, False)
+        return y, y
 
-    def _encode(self, x, in_kpm):
-        p, H = self._p(), self.num_head
+    def _ffn(self, layer, x_r, tf):
+        h = ops.linear(x_r, layer.linear1.weight, layer.linear1.bias, relu=True, p_drop=self._p(), tf32=tf, round_out=True)
+        return ops.linear(h, layer.linear2.weight, layer.linear2.bias, tf32=tf, round_dx=True)
+
+    def _encode(self, x, x_r, in_kpm):
+        p, H, tf = self._p(), self.num_head, self._tf32()
         for layer in self.encoder.layers:
             sa = layer.self_attn
-            qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
-            a = ops.SelfAttention.apply(qkv, in_kpm, H, False, p, self._impl())
-            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias)
-            x = ops.AddLayerNorm.apply(x, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
-            x = ops.AddLayerNorm.apply(x, self._ffn(layer, x), layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
+            qkv = ops.linear(x_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True)
+            a = ops.SelfAttention.apply(qkv, in_kpm, H, False, p, self._impl(), tf)
+            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, tf32=tf, round_dx=True)
+            x, x_r = self._add_ln(x, a, layer.norm1, self.layer_eps, p, tf)
+            x, x_r = self._add_ln(x, self._ffn(layer, x_r, tf), layer.norm2, self.layer_eps, p, tf)
         if self.encoder.norm is not None:
-            x = ops.AddLayerNorm.apply(x, None, self.encoder.norm.weight, self.encoder.norm.bias, 1e-5, 0.0)
-        return x
+            x, x_r = self._add_ln(x, None, self.encoder.norm, 1e-5, 0.0, tf)
+        return x, x_r
 
-    def _decode_train(self, y, memory, in_kpm, out_kpm):
-        p, H, d = self._p(), self.num_head, self.num_model
+    def _decode_train(self, y, y_r, memory_r, in_kpm, out_kpm):
+        p, H, d, tf = self._p(), self.num_head, self.num_model, self._tf32()
         for layer in self.decoder.layers:
             sa, ca = layer.self_attn, layer.multihead_attn
-            qkv = ops.linear(y, sa.in_proj_weight, sa.in_proj_bias)
-            a = ops.SelfAttention.apply(qkv, out_kpm, H, True, p, self._impl())
-            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias)
-            y = ops.AddLayerNorm.apply(y, a, layer.norm1.weight, layer.norm1.bias, self.layer_eps, p)
-            q = ops.linear(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
-            kv = ops.linear(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:])
-            a = ops.CrossAttention.apply(q, kv, in_kpm, H, p, self._impl())
-            a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias)
-            y = ops.AddLayerNorm.apply(y, a, layer.norm2.weight, layer.norm2.bias, self.layer_eps, p)
-            y = ops.AddLayerNorm.apply(y, self._ffn(layer, y), layer.norm3.weight, layer.norm3.bias, self.layer_eps, p)
-        return ops.AddLayerNorm.apply(y, None, self.decoder.norm.weight, self.decoder.norm.bias, 1e-5, 0.0)
+            qkv = ops.linear(y_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True)
+            a = ops.SelfAttention.apply(qkv, out_kpm, H, True, p, self._impl(), tf)
+            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, tf32=tf, round_dx=True)
+            y, y_r = self._add_ln(y, a, layer.norm1, self.layer_eps, p, tf)
+            q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True)
+            kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True)
+            a = ops.CrossAttention.apply(q, kv, in_kpm, H, p, self._impl(), tf)
+            a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias, tf32=tf, round_dx=True)
+            y, y_r = self._add_ln(y, a, layer.norm2, self.layer_eps, p, tf)
+            y, y_r = self._add_ln(y, self._ffn(layer, y_r, tf), layer.norm3, self.layer_eps, p, tf)
+        return self._add_ln(y, None, self.decoder.norm, 1e-5, 0.0, tf)
 
-    def _heads(self, h):
-        lv = ops.linear(h, self.vocab_head.weight, self.vocab_head.bias)
-        pf = ops.linear(h, self.pointer_head.weight, self.pointer_head.bias)
+    def _heads(self, h, h_r):
+        tf = self._tf32()
+        lv = ops.linear(h_r, self.vocab_head.weight, self.vocab_head.bias, tf32=tf)
+        pf = ops.linear(h_r, self.pointer_head.weight, self.pointer_head.bias, tf32=tf)
         lp = torch.bmm(pf, h.transpose(1, 2))                      # raw scores; 1/d applied in the kernel
         sw = F.linear(h, self.switch_head.weight, self.switch_head.bias).squeeze(-1)
         return lv, lp, sw
@@ -189,13 +203,18 @@ class PlankModel(nn.Module):
         out_kpm = self._kpm(batch['output_mask'])
         output_value, output_label = batch['output_value'], batch['output_label']
         T = output_value.shape[1]
+        tf = self._tf32()
 
-        x = self._embed_input(inputs)
-        y = self._embed_output(output_value, T)
-        memory = self._encode(x, in_kpm)
-        hiddens = self._decode_train(y, memory, in_kpm, out_kpm)
-        lv, lp, sw = self._heads(hiddens)
-        loss, accuracy, predict = ops.DistLoss.apply(lv, lp, sw, output_label, self.token.PAD, 1.0 / self.num_model)
+        if tf:
+            x, x_r = self._embed_input(inputs, True)
+            y, y_r = self._embed_output(output_value, T, True)
+        else:
+            x = x_r = self._embed_input(inputs)
+            y = y_r = self._embed_output(output_value, T)
+        memory, memory_r = self._encode(x, x_r, in_kpm)
+        hiddens, hiddens_r = self._decode_train(y, y_r, memory_r, in_kpm, out_kpm)
+        lv, lp, sw = self._heads(hiddens, hiddens_r)
+        loss, accuracy, predict = ops.DistLoss.apply(lv, lp, sw, output_label, self.token.PAD, 1.0 / self.num_model, tf)
         rets = {'loss': loss, 'accuracy': accuracy}
         if return_dists:                                           # parity tests only
             rets.update(dists=ops.dist_train_full(lv, lp, sw, 1.0 / self.num_model), hiddens=hiddens, memory=memory,
@@ -214,7 +233,8 @@ class PlankModel(nn.Module):
         """Greedy decoding with persistent K/V caches (same tokens as ref models.py:267-323)."""
         inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
         in_kpm = self._kpm(batch['input_mask'])
-        memory = self._encode(self._embed_input(inputs), in_kpm)
+        x = self._embed_input(inputs)
+        memory, _ = self._encode(x, x, in_kpm)
         if self._decoder_engine is None:
             self._decoder_engine = GreedyDecoder(self)
         output, attach = self._decoder_engine.run(memory, in_kpm)

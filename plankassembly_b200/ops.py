@@ -61,95 +61,103 @@ class EmbedInput(Function):
     """K1 (ref models.py:103-112)."""
 
     @staticmethod
-    def forward(ctx, n_tables, *args):
+    def forward(ctx, n_tables, want_r, *args):
         ids, tables = args[:n_tables], args[n_tables:]
         _require_cuda(*ids, *tables)
         ids = [i.contiguous() for i in ids]
         B, S = ids[0].shape
         d = tables[0].shape[1]
         out = torch.empty(B, S, d, device=tables[0].device, dtype=torch.float32)
+        out_r = torch.empty_like(out) if want_r else None
         call('pa_embed_input_fwd', _ptr_array([i.data_ptr() for i in ids]), _ptr_array([t.data_ptr() for t in tables]),
-             n_tables, B * S, d, out.data_ptr(), _stream())
+             n_tables, B * S, d, out.data_ptr(), _ptr(out_r), _stream())
         ctx.ids = ids
         ctx.shapes = [t.shape for t in tables]
         ctx.n = n_tables
-        return out
+        return (out, out_r) if want_r else out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout):
-        dout = dout.contiguous()
+    def backward(ctx, dout, dout_r=None):
+        dout = dout.contiguous() if dout_r is None else dout + dout_r
         grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes]
         rows = (C.c_int * ctx.n)(*[s[0] for s in ctx.shapes])
         B, S = ctx.ids[0].shape
         call('pa_embed_input_bwd', dout.data_ptr(), _ptr_array([i.data_ptr() for i in ctx.ids]),
              _ptr_array([g.data_ptr() for g in grads]), rows, ctx.n, B * S, dout.shape[-1], _stream())
-        return (None, *([None] * ctx.n), *grads)
+        return (None, None, *([None] * ctx.n), *grads)
 
 
 class EmbedOutput(Function):
     """K2 (ref models.py:114-138): value[:, :T-1] shifted right by one behind a zero row."""
 
     @staticmethod
-    def forward(ctx, value, T, dof, e_val, e_coord, e_pos):
+    def forward(ctx, value, T, dof, want_r, e_val, e_coord, e_pos):
         _require_cuda(value, e_val)
         assert value.stride(1) == 1
         B, d = value.shape[0], e_val.shape[1]
         out = torch.empty(B, T, d, device=e_val.device, dtype=torch.float32)
+        out_r = torch.empty_like(out) if want_r else None
         call('pa_embed_output_fwd', value.data_ptr(), value.stride(0), B, T, dof, e_val.data_ptr(), e_coord.data_ptr(),
-             e_pos.data_ptr(), d, out.data_ptr(), _stream())
+             e_pos.data_ptr(), d, out.data_ptr(), _ptr(out_r), _stream())
         ctx.value, ctx.T, ctx.dof = value, T, dof
         ctx.shapes = (e_val.shape, e_coord.shape, e_pos.shape)
-        return out
+        return (out, out_r) if want_r else out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout):
-        dout = dout.contiguous()
+    def backward(ctx, dout, dout_r=None):
+        dout = dout.contiguous() if dout_r is None else dout + dout_r
         gv, gc, gp = (torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes)
         call('pa_embed_output_bwd', dout.data_ptr(), ctx.value.data_ptr(), ctx.value.stride(0), dout.shape[0], ctx.T,
              ctx.dof, gv.data_ptr(), gc.data_ptr(), gp.data_ptr(), dout.shape[-1], _stream())
-        return None, None, None, gv, gc, gp
+        return None, None, None, None, gv, gc, gp
 
 
 class AddLayerNorm(Function):
-    """y = LayerNorm_eps(x + dropout_p(a)); a may be None (final norms)."""
+    """y = LayerNorm_eps(x + dropout_p(a)); a may be None (final norms).
+    want_r: also return the TF32-rounded copy of y that feeds the next tensor-core GEMM;
+    round_da: the gradient wrt a feeds tensor-core GEMMs only, so it is written rounded."""
 
     @staticmethod
-    def forward(ctx, x, a, gamma, beta, eps, p_drop):
+    def forward(ctx, x, a, gamma, beta, eps, p_drop, want_r=False, round_da=False):
         _require_cuda(x, gamma)
         x = x.contiguous()
         a = a.contiguous() if a is not None else None
         d = x.shape[-1]
         rows = x.numel() // d
         y = torch.empty_like(x)
+        y_r = torch.empty_like(x) if want_r else None
         need_grad = any(ctx.needs_input_grad)
         s = torch.empty_like(x) if (need_grad and a is not None) else None
         stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
         seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
         call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
-             seed, off, rows, d, y.data_ptr(), _ptr(s), _ptr(stats), _stream())
+             seed, off, rows, d, y.data_ptr(), _ptr(y_r), _ptr(s), _ptr(stats), _stream())
         ctx.save_for_backward(s if s is not None else x, stats, gamma)
         ctx.has_a, ctx.p, ctx.seed, ctx.off = a is not None, (p_drop if a is not None else 0.0), seed, off
-        return y
+        ctx.round_da = round_da
+        return (y, y_r) if want_r else y
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy_r=None):
         s, stats, gamma = ctx.saved_tensors
         dy = dy.contiguous()
+        dy_r = dy_r.contiguous() if dy_r is not None else None
         d = s.shape[-1]
         rows = s.numel() // d
         dx = torch.empty_like(s)
-        da = torch.empty_like(s) if (ctx.has_a and ctx.p > 0) else None
+        da = torch.empty_like(s) if (ctx.has_a and (ctx.p > 0 or ctx.round_da)) else None
         dgamma = torch.zeros_like(gamma)
         dbeta = torch.zeros_like(gamma)
         ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=s.device, dtype=torch.uint8)
-        call('pa_add_ln_bwd', dy.data_ptr(), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed, ctx.off,
-             rows, d, dx.data_ptr(), _ptr(da), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _stream(), launches=2)
+        call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed,
+             ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
+             _stream(), launches=2)
         if ctx.has_a and da is None:
-            da = dx                      # no dropout: same gradient flows to both summands
-        return dx, (da if ctx.has_a else None), dgamma, dbeta, None, None
+            da = dx                      # no dropout, no rounding: same gradient flows to both summands
+        return dx, (da if ctx.has_a else None), dgamma, dbeta, None, None, None, None
 
 
 class ReluDropout(Function):
@@ -171,24 +179,24 @@ class ReluDropout(Function):
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
         g = g.contiguous().clone()
-        call('pa_relu_dropout_bwd', out.data_ptr(), g.data_ptr(), g.numel(), ctx.p, _stream())
+        call('pa_relu_dropout_bwd', out.data_ptr(), g.data_ptr(), g.numel(), ctx.p, 0, _stream())
         return g, None
 
 
-def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, seed, off, impl, want_lse, device):
+def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, seed, off, impl, want_lse, device, rnd=False):
     o = torch.empty(B, Lq, H * dh, device=device, dtype=torch.float32)
     lse = torch.empty(B, H, Lq, device=device, dtype=torch.float32) if want_lse else None
     a = AttnFwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), H * dh, _ptr(lse), _ptr(kpm), B, H, Lq, Lk, dh, int(causal),
-                    dh ** -0.5, p_drop, seed, off, impl)
+                    dh ** -0.5, p_drop, seed, off, impl, int(rnd))
     call('pa_attn_fwd', C.byref(a), _stream())
     return o, lse
 
 
 def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, B, H, Lq, Lk, dh, kpm, causal, p_drop,
-              seed, off, impl):
+              seed, off, impl, rnd=False):
     delta = torch.empty(B, H, Lq, device=o.device, dtype=torch.float32)
     a = AttnBwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), do.data_ptr(), H * dh, lse.data_ptr(), delta.data_ptr(),
-                    dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl)
+                    dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl, int(rnd))
     call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
 
 
@@ -196,7 +204,7 @@ class SelfAttention(Function):
     """K3/K4: attention core over the packed in-projection output qkv [B,L,3d]."""
 
     @staticmethod
-    def forward(ctx, qkv, kpm, H, causal, p_drop, impl):
+    def forward(ctx, qkv, kpm, H, causal, p_drop, impl, rnd=False):
         _require_cuda(qkv)
         qkv = qkv.contiguous()
         B, L, d3 = qkv.shape
@@ -204,30 +212,30 @@ class SelfAttention(Function):
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
         base = qkv.data_ptr()
         o, lse = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
-                           impl, any(ctx.needs_input_grad), qkv.device)
+                           impl, any(ctx.needs_input_grad), qkv.device, rnd)
         ctx.save_for_backward(qkv, o, lse, kpm)
-        ctx.cfg = (H, causal, p_drop, seed, off, impl)
+        ctx.cfg = (H, causal, p_drop, seed, off, impl, rnd)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
         qkv, o, lse, kpm = ctx.saved_tensors
-        H, causal, p_drop, seed, off, impl = ctx.cfg
+        H, causal, p_drop, seed, off, impl, rnd = ctx.cfg
         B, L, d3 = qkv.shape
         d = d3 // 3
         dqkv = torch.empty_like(qkv)
         base, g = qkv.data_ptr(), dqkv.data_ptr()
         _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
-                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, 0)
-        return dqkv, None, None, None, None, None
+                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, 0, rnd)
+        return dqkv, None, None, None, None, None, None
 
 
 class CrossAttention(Function):
     """K5: queries q [B,Lq,d] against the packed memory projection kv [B,Lk,2d]."""
 
     @staticmethod
-    def forward(ctx, q, kv, kpm, H, p_drop, impl):
+    def forward(ctx, q, kv, kpm, H, p_drop, impl, rnd=False):
         _require_cuda(q, kv)
         q, kv = q.contiguous(), kv.contiguous()
         B, Lq, d = q.shape
@@ -236,30 +244,31 @@ class CrossAttention(Function):
         kb = kv.data_ptr()
         need = any(ctx.needs_input_grad)
         o, lse = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
-                           impl, need, q.device)
+                           impl, need, q.device, rnd)
         ctx.save_for_backward(q, kv, o, lse, kpm)
-        ctx.cfg = (H, p_drop, seed, off, impl)
+        ctx.cfg = (H, p_drop, seed, off, impl, rnd)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
         q, kv, o, lse, kpm = ctx.saved_tensors
-        H, p_drop, seed, off, impl = ctx.cfg
+        H, p_drop, seed, off, impl, rnd = ctx.cfg
         B, Lq, d = q.shape
         Lk = kv.shape[1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         kb, gb = kv.data_ptr(), dkv.data_ptr()
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
-                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, 0)
-        return dq, dkv, None, None, None, None
+                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, 0, rnd)
+        return dq, dkv, None, None, None, None, None
 
 
 def gemm_tf32(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, bias=None, relu=False, p_drop=0.0, seed=0, off=0,
-              alpha=1.0, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, split_k=1, accumulate=False):
+              alpha=1.0, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, split_k=1, accumulate=False, round_out=False):
     """C = alpha * op(A) op(B)^T (+bias)(relu)(dropout) on the tcgen05 tensor cores (TF32 in, FP32 acc)."""
     g = GemmArgs(a.data_ptr(), lda, int(a_mn), b.data_ptr(), ldb, int(b_mn), c.data_ptr(), ldc, _ptr(bias), int(relu), p_drop,
-                 seed, off, alpha, M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, split_k, int(accumulate))
+                 seed, off, alpha, M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, split_k, int(accumulate),
+                 int(round_out))
     call('pa_gemm_tf32', C.byref(g), _stream())
     return c
 
@@ -270,40 +279,58 @@ def _split_k(tiles, k_blocks):
     return max(1, min(sk, k_blocks // 8 if k_blocks >= 8 else 1))
 
 
+_W_TF32 = {}
+
+
+def tf32_weight(W):
+    """TF32-rounded shadow copy of a parameter, refreshed when the optimizer has stepped (version bump)."""
+    key = id(W)
+    ent = _W_TF32.get(key)
+    if ent is None or ent[0] != W._version or ent[1].device != W.device or ent[2] is not W:
+        buf = ent[1] if (ent is not None and ent[1].shape == W.shape and ent[1].device == W.device) else torch.empty_like(W)
+        call('pa_round_tf32', W.data_ptr(), buf.data_ptr(), W.numel(), _stream())
+        ent = (W._version, buf, W)
+        _W_TF32[key] = ent
+    return ent[1]
+
+
 class Linear(Function):
-    """y = x W^T + b (optionally relu + dropout fused in the GEMM epilogue), TF32 tensor cores.
-    Backward: dx = dy W  (B operand MN-major: W as stored), dW = dy^T x (both operands MN-major,
-    split-K over the tokens with fp32 RED), db = column sums of dy."""
+    """y = x W^T + b (optionally relu + dropout fused in the GEMM epilogue) on the TF32 tensor cores.
+    x must already be TF32-rounded by its producer; W_r is the rounded shadow of W (W itself only routes
+    the gradient).  Backward: dx = dy W_r (B operand MN-major: W as stored), dW = dy^T x (both operands
+    MN-major, split-K over the tokens with fp32 RED), db = column sums of dy.
+    round_out / round_dx: y / dx feed tensor-core operands only and are written rounded."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu, p_drop):
+    def forward(ctx, x, W, b, W_r, relu, p_drop, round_out, round_dx):
         _require_cuda(x, W)
         K, N = W.shape[1], W.shape[0]
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        assert W.stride(1) == 1
+        assert W_r.stride(1) == 1
         M = x2.shape[0]
         y = torch.empty(M, N, device=x.device, dtype=torch.float32)
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
-        gemm_tf32(x2, W, y, M, N, K, lda=K, ldb=W.stride(0), ldc=N, bias=b, relu=relu, p_drop=p_drop, seed=seed, off=off)
-        ctx.save_for_backward(x2, W, y if (relu or p_drop > 0) else None)
-        ctx.cfg = (relu, p_drop, b is not None, x.shape)
+        gemm_tf32(x2, W_r, y, M, N, K, lda=K, ldb=W_r.stride(0), ldc=N, bias=b, relu=relu, p_drop=p_drop, seed=seed, off=off,
+                  round_out=round_out)
+        ctx.save_for_backward(x2, W_r, y if (relu or p_drop > 0) else None)
+        ctx.cfg = (relu, p_drop, b is not None, x.shape, round_dx)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x2, W, y = ctx.saved_tensors
-        relu, p_drop, has_b, xshape = ctx.cfg
-        N, K = W.shape
+        x2, W_r, y = ctx.saved_tensors
+        relu, p_drop, has_b, xshape, round_dx = ctx.cfg
+        N, K = W_r.shape
         M = x2.shape[0]
         dy2 = dy.reshape(M, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         if y is not None:
             dy2 = dy2.clone()
-            call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, _stream())
+            call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, 1, _stream())
         db = dy2.sum(0) if (has_b and ctx.needs_input_grad[2]) else None
         ldn = N
         if N % 4:                         # TMA needs a 16-byte row pitch (vocab head: N = 514)
@@ -312,24 +339,29 @@ class Linear(Function):
         dx = dW = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
-            gemm_tf32(dy2, W, dx, M, K, N, lda=ldn, ldb=W.stride(0), ldc=K, b_mn=True)
+            gemm_tf32(dy2, W_r, dx, M, K, N, lda=ldn, ldb=W_r.stride(0), ldc=K, b_mn=True, round_out=round_dx)
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1]:
             dW = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
             tiles = ((N + 127) // 128) * ((K + 127) // 128)
             gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
-        return dx, dW, db, None, None
+        return dx, dW, db, None, None, None, None, None
 
 
 GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 
 
-def linear(x, W, b, relu=False, p_drop=0.0):
-    """Dense projection used by the model: our tcgen05 GEMM ('tc') or cuBLAS fp32 ('cublas')."""
-    if os.environ.get('PLANK_B200_GEMM', GEMM_IMPL) == 'tc':
-        return Linear.apply(x, W, b, relu, p_drop)
-    y = torch.nn.functional.linear(x, W, b)
+def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False):
+    """Dense projection y = x W[rows]^T + b[rows].
+    tf32=True : our tcgen05 TF32 GEMM (training path; x must be a TF32-rounded tensor).
+    tf32=False: cuBLAS fp32 through torch (exact path used by inference and PLANK_B200_GEMM=cublas)."""
+    Wv = W if rows is None else W[rows]
+    bv = b if (rows is None or b is None) else b[rows]
+    if tf32:
+        W_r = tf32_weight(W)
+        return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx)
+    y = torch.nn.functional.linear(x, Wv, bv)
     if relu:
         y = ReluDropout.apply(y, p_drop)
     return y
@@ -340,7 +372,7 @@ class DistLoss(Function):
     lp holds the RAW pointer scores pf.h^T; the kernel applies 1/d and the 1e-6 fill."""
 
     @staticmethod
-    def forward(ctx, lv, lp, sw, label, pad, inv_d):
+    def forward(ctx, lv, lp, sw, label, pad, inv_d, rnd=False):
         _require_cuda(lv, lp, sw, label)
         lv, lp, sw, label = lv.contiguous(), lp.contiguous(), sw.contiguous(), label.contiguous()
         B, T, V = lv.shape
@@ -352,7 +384,7 @@ class DistLoss(Function):
         loss = accum[0] / accum[1]
         accuracy = accum[2] / (accum[1] + 1e-10)
         ctx.save_for_backward(lv, lp, sw, label, rowstat, accum)
-        ctx.cfg = (pad, inv_d)
+        ctx.cfg = (pad, inv_d, rnd)
         ctx.mark_non_differentiable(accuracy, predict)
         return loss, accuracy, predict
 
@@ -360,13 +392,14 @@ class DistLoss(Function):
     @once_differentiable
     def backward(ctx, gloss, _gacc, _gpred):
         lv, lp, sw, label, rowstat, accum = ctx.saved_tensors
-        pad, inv_d = ctx.cfg
+        pad, inv_d, rnd = ctx.cfg
         B, T, V = lv.shape
         dlv, dlp, dsw = torch.empty_like(lv), torch.empty_like(lp), torch.empty_like(sw)
         gloss = gloss.contiguous().to(torch.float32)
         call('pa_dist_loss_bwd', lv.data_ptr(), lp.data_ptr(), sw.data_ptr(), label.data_ptr(), rowstat.data_ptr(),
-             accum.data_ptr(), gloss.data_ptr(), B, T, V, pad, inv_d, dlv.data_ptr(), dlp.data_ptr(), dsw.data_ptr(), _stream())
-        return dlv, dlp, dsw, None, None, None
+             accum.data_ptr(), gloss.data_ptr(), B, T, V, pad, inv_d, dlv.data_ptr(), dlp.data_ptr(), dsw.data_ptr(), int(rnd),
+             _stream())
+        return dlv, dlp, dsw, None, None, None, None
 
 
 def dist_train_full(lv, lp, sw, inv_d):

@@ -104,7 +104,7 @@ def test_linear_autograd_matches_torch():
     gy = torch.randn(B, L, N, generator=g, dtype=torch.float64)
     (ref * gy).sum().backward()
     cx, cw, cb = (t.detach().float().cuda().requires_grad_(True) for t in (x, w, b))
-    out = ops.Linear.apply(cx, cw, cb, False, 0.0)
+    out = ops.Linear.apply(cx, cw, cb, cw.detach(), False, 0.0, False, False)
     assert rel_err(out.cpu(), ref.detach()) < 2e-3
     (out * gy.float().cuda()).sum().backward()
     assert rel_err(cx.grad.cpu(), x.grad) < 2e-3
@@ -124,8 +124,31 @@ def test_linear_vocab_head_shape():
     gy = torch.randn(M, N, generator=g, dtype=torch.float64)
     (ref * gy).sum().backward()
     cx, cw, cb = (t.detach().float().cuda().requires_grad_(True) for t in (x, w, b))
-    out = ops.Linear.apply(cx, cw, cb, False, 0.0)
+    out = ops.Linear.apply(cx, cw, cb, cw.detach(), False, 0.0, False, False)
     assert rel_err(out.cpu(), ref.detach()) < 2e-3
     (out * gy.float().cuda()).sum().backward()
     assert rel_err(cx.grad.cpu(), x.grad) < 2e-3
     assert rel_err(cw.grad.cpu(), w.grad) < 2e-3
+
+
+def test_rounded_operands_remove_truncation_bias():
+    """Operands rounded to nearest TF32 by the producer (pa_round_tf32 / epilogue flags) give an
+    unbiased product: the error vs fp64 drops well below the ~7.5e-4 of raw (truncated) operands."""
+    from plankassembly_b200 import ops
+    from plankassembly_b200._lib import call
+    g = torch.Generator().manual_seed(7)
+    M, N, K = 2048, 512, 512
+    a, w = torch.randn(M, K, generator=g).cuda(), (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    ar, wr = torch.empty_like(a), torch.empty_like(w)
+    st = torch.cuda.current_stream().cuda_stream
+    call('pa_round_tf32', a.data_ptr(), ar.data_ptr(), a.numel(), st)
+    call('pa_round_tf32', w.data_ptr(), wr.data_ptr(), w.numel(), st)
+    assert torch.equal(ar.view(torch.int32) & 0x1FFF, torch.zeros_like(ar, dtype=torch.int32))
+    assert (ar - a).abs().max() <= a.abs().max() * 2.0 ** -11
+    c_raw, c_rn = torch.empty(M, N, device='cuda'), torch.empty(M, N, device='cuda')
+    ops.gemm_tf32(a, w, c_raw, M, N, K, lda=K, ldb=K, ldc=N)
+    ops.gemm_tf32(ar, wr, c_rn, M, N, K, lda=K, ldb=K, ldc=N)
+    ref = a.double().cpu() @ w.double().cpu().T
+    e_raw, e_rn = rel_err(c_raw.cpu(), ref), rel_err(c_rn.cpu(), ref)
+    print(f'raw (truncated) operands: {e_raw:.2e}; round-to-nearest operands: {e_rn:.2e}')
+    assert e_rn < 0.5 * e_raw and e_rn < 4e-4

@@ -34,7 +34,7 @@ def test_embed_input_fwd_bwd(ops, n_tables, d):
     w = torch.randn(B, S, d, generator=g)
     (ref * w).sum().backward()
     ctabs = [t.detach().to(dev()).requires_grad_(True) for t in tabs]
-    out = ops.EmbedInput.apply(n_tables, *[i.to(dev()) for i in ids], *ctabs)
+    out = ops.EmbedInput.apply(n_tables, False, *[i.to(dev()) for i in ids], *ctabs)
     assert rel_err(out.cpu(), ref.detach()) < 1e-6
     (out * w.to(dev())).sum().backward()
     for a, b in zip(ctabs, tabs):
@@ -53,7 +53,7 @@ def test_embed_output_fwd_bwd(ops):
     w = torch.randn(B, T, d, generator=g)
     (ref * w).sum().backward()
     cv, cc, cp = (x.detach().to(dev()).requires_grad_(True) for x in (ev, ec, ep))
-    out = ops.EmbedOutput.apply(value.to(dev()), T, dof, cv, cc, cp)
+    out = ops.EmbedOutput.apply(value.to(dev()), T, dof, False, cv, cc, cp)
     assert torch.equal(out.cpu()[:, 0], torch.zeros(B, d))
     assert rel_err(out.cpu(), ref.detach()) < 1e-6
     (out * w.to(dev())).sum().backward()
