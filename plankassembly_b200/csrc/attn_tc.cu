@@ -1,8 +1,339 @@
-// Tensor-core (tcgen05, TF32) attention forward -- placeholder until the kernel lands.
+// K3/K4/K5 on the 5th-gen tensor cores: flash-style attention forward, TF32 operands, FP32 accumulate.
+//
+//   S = Q K^T   : tcgen05.mma kind::tf32, A = Q tile (smem, K-major, 128B swizzle), B = K tile (smem, K-major)
+//   P = softmax : one thread per query row reads its S row from TMEM (tcgen05.ld), applies scale +
+//                 key-padding / causal masks + online max/sum + Philox dropout in registers, rounds
+//                 P to nearest TF32 and writes it back over S in TMEM (tcgen05.st)
+//   O_j = P V   : tcgen05.mma with A = P straight from TMEM, B = V tile (smem, MN-major, 128B_BASE32B)
+//   O += O_j    : rescaled accumulation in registers (no TMEM read-modify-write of O)
+//
+// Persistent CTAs (one per SM), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = softmax/accumulate warpgroup (128 threads = 128 query rows = 128 TMEM lanes).
+// Pipelines: K ring (3 stages) and V ring (2 stages) fed by TMA; S/P and O double-buffered in TMEM so
+// QK^T of tile j+1 and P V of tile j overlap the softmax of tile j.
+//   Reference: torch nn/functional.py multi_head_attention_forward as reached from ref models.py:206,212.
 #include "common.cuh"
+#include "tc_common.cuh"
 
+namespace {
+
+constexpr int BQ = 128, BKV = 128;
+constexpr int kThreads = 192;
+constexpr int kKStages = 3, kVStages = 2;
+
+template <int DH> struct Cfg {
+  static constexpr int kChunks = DH / 32;                 // 32-float (128 B) column chunks per row
+  static constexpr int kTileBytes = kChunks * BQ * 128;   // one Q / K / V tile
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kTileBytes;
+  static constexpr int kOffV = kOffK + kKStages * kTileBytes;
+  static constexpr int kOffBias = kOffV + kVStages * kTileBytes;
+  static constexpr int kOffBar = kOffBias + 2 * BKV * 4;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColS = 0;                          // 2 x 128 columns  S / P
+  static constexpr int kColO = 256;                        // 2 x DH columns   O_j
+};
+
+struct Params {
+  float* o; int64_t ldo; float* lse; const uint8_t* kpm;
+  int B, H, Lq, Lk, causal, round_out;
+  float scale_log2;   // scale * log2(e)
+  float p_drop; uint64_t seed, offset;
+  int q_tiles, items;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const Params p) {
+  using C = Cfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;            // [3]
+  uint64_t* k_empty = bars + 5;           // [3]
+  uint64_t* v_full = bars + 8;            // [2]
+  uint64_t* v_empty = bars + 10;          // [2]
+  uint64_t* s_full = bars + 12;           // [2]
+  uint64_t* p_full = bars + 14;           // [2]
+  uint64_t* o_full = bars + 16;           // [2]
+  uint64_t* o_empty = bars + 18;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
+    for (int s = 0; s < kKStages; ++s) { tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1); }
+    for (int s = 0; s < kVStages; ++s) { tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 4);
+      tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto item_coords = [&](int item, int& b, int& h, int& q0, int& ntiles) {
+    int qt = item % p.q_tiles;
+    int bh = item / p.q_tiles;
+    h = bh % p.H; b = bh / p.H;
+    q0 = qt * BQ;
+    int all = (p.Lk + BKV - 1) / BKV;
+    ntiles = p.causal ? min(all, qt + 1) : all;
+  };
+
+  if (warp == 0) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      uint32_t kc = 0, vc = 0, ic = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, q0, n;
+        item_coords(item, b, h, q0, n);
+        tc::mbar_wait(q_empty, (ic & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(q_full, C::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) tc::tma_load_2d(smem + C::kOffQ + c * (BQ * 128), &tm_q, h * DH + c * 32, b * p.Lq + q0, q_full);
+        for (int j = 0; j < n; ++j) {
+          const int ks = kc % kKStages;
+          tc::mbar_wait(k_empty + ks, ((kc / kKStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(k_full + ks, C::kTileBytes);
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c)
+            tc::tma_load_2d(smem + C::kOffK + ks * C::kTileBytes + c * (BKV * 128), &tm_k, h * DH + c * 32, b * p.Lk + j * BKV, k_full + ks);
+          ++kc;
+          const int vs = vc % kVStages;
+          tc::mbar_wait(v_empty + vs, ((vc / kVStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(v_full + vs, C::kTileBytes);
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c)
+            tc::tma_load_2d(smem + C::kOffV + vs * C::kTileBytes + c * (BKV * 128), &tm_v, h * DH + c * 32, b * p.Lk + j * BKV, v_full + vs);
+          ++vc;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================= MMA issuer =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::make_idesc_tf32(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = tc::make_idesc_tf32(BQ, DH, 0, 1);
+      uint32_t kc = 0, vc = 0, st = 0 /*QK tiles issued*/, pt = 0 /*PV tiles issued*/, ic = 0;
+      const uint32_t sq = tc::smem_u32(smem + C::kOffQ);
+      auto issue_qk = [&]() {
+        const int ks = kc % kKStages;
+        tc::mbar_wait(k_full + ks, (kc / kKStages) & 1);
+        tc::tc_fence_after();
+        const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes);
+        const uint32_t d_tmem = tmem_base + C::kColS + (st & 1) * BKV;
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint64_t dq = tc::make_smem_desc(sq + c * (BQ * 128), 16, 1024);
+          const uint64_t dk = tc::make_smem_desc(sk + c * (BKV * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_tf32_ss(d_tmem, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::tc_commit(k_empty + ks);
+        tc::tc_commit(s_full + (st & 1));
+        ++kc; ++st;
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, q0, n;
+        item_coords(item, b, h, q0, n);
+        tc::mbar_wait(q_full, ic & 1);
+        tc::tc_fence_after();
+        issue_qk();
+        if (n > 1) issue_qk();
+        if (n <= 2) tc::tc_commit(q_empty);
+        for (int j = 0; j < n; ++j) {
+          const int buf = pt & 1;
+          tc::mbar_wait(p_full + buf, (pt >> 1) & 1);
+          tc::mbar_wait(o_empty + buf, ((pt >> 1) & 1) ^ 1);
+          const int vs = vc % kVStages;
+          tc::mbar_wait(v_full + vs, (vc / kVStages) & 1);
+          tc::tc_fence_after();
+          const uint32_t sv = tc::smem_u32(smem + C::kOffV + vs * C::kTileBytes);
+          // V tile: kChunks MN blocks (32 head-dim columns each) of 128 key rows x 128 B; 4-row swizzle atoms
+          const uint64_t dv = tc::make_smem_desc(sv, BKV * 128, 512, tc::kLayoutSw128Base32);
+          const uint32_t a_tmem = tmem_base + C::kColS + buf * BKV;
+          const uint32_t d_tmem = tmem_base + C::kColO + buf * DH;
+#pragma unroll
+          for (int k = 0; k < BKV / 8; ++k)
+            tc::mma_tf32_ts(d_tmem, a_tmem + k * 8, tc::desc_advance(dv, k * 1024), idesc_pv, k > 0 ? 1u : 0u);
+          tc::tc_commit(v_empty + vs);
+          tc::tc_commit(o_full + buf);
+          ++vc; ++pt;
+          if (j + 2 < n) {
+            issue_qk();
+            if (j + 3 == n) tc::tc_commit(q_empty);      // that was the last QK^T of this item
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ softmax / accumulate warpgroup ================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int tid = threadIdx.x - 64;                    // 0..127
+    const uint32_t thr = drop_threshold(p.p_drop);
+    const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int Lk4 = (p.Lk + 3) / 4;
+    uint32_t sc = 0, oc = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, h, q0, n;
+      item_coords(item, b, h, q0, n);
+      const int qi = q0 + row;
+      const int64_t row_global = ((int64_t)(b * p.H + h) * p.Lq + qi);
+      float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+      float o_acc[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) o_acc[c] = 0.f;
+
+      auto accumulate_o = [&]() {
+        const int obuf = oc & 1;
+        tc::mbar_wait(o_full + obuf, (oc >> 1) & 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColO + obuf * DH + c0, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o_acc[c0 + c] = o_acc[c0 + c] * corr_prev + __uint_as_float(r[c]);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(o_empty + obuf);
+        ++oc;
+      };
+
+      for (int j = 0; j < n; ++j) {
+        const int buf = sc & 1;
+        const int k0 = j * BKV;
+        {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
+          const int kj = k0 + tid;
+          const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+          bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tc::mbar_wait(s_full + buf, (sc >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV;
+        float s[BKV];
+#pragma unroll
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(s_addr + c0, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) s[c0 + c] = __uint_as_float(r[c]);
+        }
+        const bool diag = p.causal && (k0 + BKV - 1 > q0);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) {
+          float v = s[c] * p.scale_log2 + bias_s[buf * BKV + c];
+          if (diag && k0 + c > qi) v = -INFINITY;
+          s[c] = v;
+          mx = fmaxf(mx, v);
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+        const float corr = exp2f(m_run - m_safe);
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - m_safe); rs += s[c]; }
+        l_run = l_run * corr + rs;
+        m_run = m_new;
+        if (p.p_drop > 0.f) {
+#pragma unroll
+          for (int c = 0; c < BKV; c += 4) {
+            uint4 rn = philox4x32(p.seed, (uint64_t)(row_global * Lk4 + ((k0 + c) >> 2)), p.offset);
+            s[c] = rn.x >= thr ? s[c] * ks : 0.f; s[c + 1] = rn.y >= thr ? s[c + 1] * ks : 0.f;
+            s[c + 2] = rn.z >= thr ? s[c + 2] * ks : 0.f; s[c + 3] = rn.w >= thr ? s[c + 3] * ks : 0.f;
+          }
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(tf32_rn(s[c0 + c]));
+          tc::tmem_st_32x32(s_addr + c0, r);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_full + buf);
+        ++sc;
+        if (j > 0) accumulate_o();        // O_{j-1}: its P V overlapped this tile's softmax
+        corr_prev = corr;
+      }
+      accumulate_o();
+      if (qi < p.Lq) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+          float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+          if (p.round_out) v = tf32_rn4(v);
+          *reinterpret_cast<float4*>(op + c) = v;
+        }
+        if (p.lse != nullptr)
+          p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int DH>
+int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
+  using C = Cfg<DH>;
+  CUtensorMap tq, tk, tv;
+  int rc = pa_make_tmap_2d(&tq, a.q, (uint64_t)a.H * DH, (uint64_t)a.B * a.Lq, (uint64_t)a.ldq * 4, 32, BQ);
+  if (rc) return rc;
+  rc = pa_make_tmap_2d(&tk, a.k, (uint64_t)a.H * DH, (uint64_t)a.B * a.Lk, (uint64_t)a.ldk * 4, 32, BKV);
+  if (rc) return rc;
+  rc = pa_make_tmap_2d(&tv, a.v, (uint64_t)a.H * DH, (uint64_t)a.B * a.Lk, (uint64_t)a.ldv * 4, 32, BKV, true);
+  if (rc) return rc;
+  Params p{};
+  p.o = a.o; p.ldo = a.ldo; p.lse = a.lse; p.kpm = a.kpm;
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.causal = a.causal; p.round_out = a.round_out;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset;
+  p.q_tiles = (a.Lq + BQ - 1) / BQ;
+  p.items = p.q_tiles * a.H * a.B;
+  auto kern = attn_fwd_tc_kernel<DH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_done = true;
+  }
+  int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  kern<<<grid, kThreads, C::kSmem, st>>>(tq, tk, tv, p);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+}  // namespace
+
+// The tensor maps address q/k/v as 2-D [B*L rows, H*dh columns] arrays (row pitch ld) from their own base
+// pointers, so the packed in-projection output [B,L,3d] is consumed in place.
 int pa_attn_fwd_tc(const pa_attn_fwd_args* a, void* stream) {
-  (void)a; (void)stream;
-  pa_set_error("pa_attn_fwd: tensor-core path not built yet");
-  return PA_ERR_UNSUPPORTED;
+  switch (a->dh) {
+    case 32: return launch<32>(*a, (cudaStream_t)stream);
+    case 64: return launch<64>(*a, (cudaStream_t)stream);
+    default: pa_set_error("pa_attn_fwd (tc): head dim %d unsupported (32, 64)", a->dh); return PA_ERR_UNSUPPORTED;
+  }
 }

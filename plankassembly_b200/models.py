@@ -92,7 +92,7 @@ class PlankModel(nn.Module):
         # the positional-argument quirk of ref models.py:60-61: eps := normalize_before, post-norm
         self.layer_eps = float(normalize_before)
         # 'simt' = fp32 CUDA-core attention (exact), 'tc' = tcgen05 TF32 attention forward
-        self.attn_impl = os.environ.get('PLANK_B200_ATTN', 'simt')
+        self.attn_impl = os.environ.get('PLANK_B200_ATTN', 'tc')
 
         self.input_embeddings = nn.ModuleDict({
             'input_value': nn.Embedding(vocab_size, num_model),
@@ -131,7 +131,8 @@ class PlankModel(nn.Module):
         return self.training and ops.GEMM_IMPL == 'tc'
 
     def _impl(self):
-        return ops.ATTN_IMPL[self.attn_impl]
+        # tensor-core attention belongs to the TF32 training path; inference stays on the exact kernels
+        return ops.ATTN_IMPL[self.attn_impl] if self._tf32() else 0
 
     @staticmethod
     def _kpm(mask):

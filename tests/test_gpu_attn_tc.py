@@ -1,0 +1,102 @@
+"""tcgen05 TF32 attention forward (pa_attn_fwd impl=1) against fp64 math.  Inputs are pre-rounded to
+TF32 (as their producers do in the model), so the only reduced-precision step left inside the kernel is
+the round-to-nearest of P before the P V contraction; tolerance 5e-4 relative (bar: 1e-3)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _util import rel_err  # noqa: E402
+from test_gpu_kernels import attn_ref  # noqa: E402
+
+TOL = 5e-4
+
+
+def tf32_round(x):
+    from plankassembly_b200._lib import call
+    xc = x.float().cuda().contiguous()
+    out = torch.empty_like(xc)
+    call('pa_round_tf32', xc.data_ptr(), out.data_ptr(), xc.numel(), torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+CASES = [  # B, H, dh, L, causal, masked tail
+    (2, 8, 64, 512, False, True), (2, 8, 64, 256, True, True), (2, 4, 32, 299, False, True), (3, 4, 32, 64, True, True),
+    (1, 8, 64, 128, False, False), (1, 8, 64, 130, True, False), (1, 2, 32, 1, True, False), (4, 8, 64, 1199, False, True),
+]
+
+
+@pytest.mark.parametrize('B,H,dh,L,causal,tail', CASES)
+def test_self_attention_tc_fwd(B, H, dh, L, causal, tail):
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    d = H * dh
+    qkv = tf32_round(torch.randn(B, L, 3 * d, generator=g))
+    kpm = torch.zeros(B, L, dtype=torch.bool)
+    if tail:
+        for b in range(B):
+            kpm[b, max(1, L - 1 - 37 * (b + 1)):] = True
+    q, k, v = qkv.double().cpu().split(d, -1)
+    ref = attn_ref(q, k, v, kpm if tail else None, causal, H)
+    ck = kpm.cuda().view(torch.uint8) if tail else None
+    out = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 1)
+    torch.cuda.synchronize()
+    err = rel_err(out.cpu(), ref)
+    exact = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 0)
+    print(f'B{B} H{H} dh{dh} L{L} causal={causal}: tc vs fp64 {err:.2e}; simt vs fp64 {rel_err(exact.cpu(), ref):.2e}')
+    assert err < TOL
+
+
+@pytest.mark.parametrize('B,H,dh,Lq,Lk', [(2, 8, 64, 256, 512), (2, 4, 32, 64, 299), (1, 8, 64, 3, 1199), (2, 4, 32, 128, 5)])
+def test_cross_attention_tc_fwd(B, H, dh, Lq, Lk):
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    d = H * dh
+    q = tf32_round(torch.randn(B, Lq, d, generator=g))
+    kv = tf32_round(torch.randn(B, Lk, 2 * d, generator=g))
+    kpm = torch.zeros(B, Lk, dtype=torch.bool)
+    for b in range(B):
+        kpm[b, max(1, Lk - 3 - 40 * b):] = True
+    k, v = kv.double().cpu().split(d, -1)
+    ref = attn_ref(q.double().cpu(), k, v, kpm, False, H)
+    out = ops.CrossAttention.apply(q, kv, kpm.cuda().view(torch.uint8), H, 0.0, 1)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu(), ref) < TOL
+
+
+def test_tc_lse_and_backward_pairing():
+    """The TC forward's LSE feeds the fp32 backward kernels: grads must match fp64 autograd."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    B, H, dh, L = 2, 8, 64, 256
+    d = H * dh
+    qkv = tf32_round(torch.randn(B, L, 3 * d, generator=g)).requires_grad_(True)
+    q64 = qkv.detach().double().cpu().requires_grad_(True)
+    q, k, v = q64.split(d, -1)
+    ref = attn_ref(q, k, v, None, True, H)
+    w = torch.randn(B, L, d, generator=g, dtype=torch.float64)
+    (ref * w).sum().backward()
+    out = ops.SelfAttention.apply(qkv, None, H, True, 0.0, 1)
+    (out * w.float().cuda()).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) < TOL
+    assert rel_err(qkv.grad.cpu(), q64.grad) < TOL
+
+
+def test_tc_dropout_matches_simt_mask():
+    """Same Philox indexing in both kernels: with V = identity the dropped probabilities are visible."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(14)
+    B, H, dh, L, p = 2, 2, 64, 64, 0.2
+    d = H * dh
+    q, k = torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)
+    v = torch.eye(L)[None, :, None, :].expand(B, L, H, dh).reshape(B, L, d)
+    qkv = tf32_round(torch.cat([q, k, v], -1))
+    ops.RNG.seed, ops.RNG.counter = 1234, 100
+    o_tc = ops.SelfAttention.apply(qkv, None, H, False, p, 1)
+    ops.RNG.seed, ops.RNG.counter = 1234, 100
+    o_simt = ops.SelfAttention.apply(qkv, None, H, False, p, 0)
+    assert torch.equal(o_tc > 0, o_simt > 0)
+    assert abs((o_tc > 0).float().mean().item() - (1 - p)) < 2e-2
+    assert rel_err(o_tc.cpu(), o_simt.cpu()) < TOL
