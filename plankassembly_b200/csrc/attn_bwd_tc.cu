@@ -1,0 +1,581 @@
+// Attention backward on the 5th-gen tensor cores (TF32 operands, FP32 accumulation in TMEM).
+// Two persistent, warp-specialised kernels (warp 0 TMA, warp 1 MMA issuer, warps 2..5 elementwise):
+//
+//  dq kernel  (query-stationary, 128 queries x 64-key steps; TMEM lanes = queries)
+//     S  = Q K_j^T,  dP = dO V_j^T                       (tcgen05.mma SS, K-major operands)
+//     dS = P o (dropout(dP) - delta),  P = exp2(S*c - lse)  in registers, written back over S in TMEM
+//     dQ += dS K_j                                        (A = dS from TMEM, B = K_j MN-major); dQ stays in
+//                                                          TMEM for the whole key loop -> one store, no atomics
+//  dkdv kernel (key-stationary, 128 keys x 64-query steps; TMEM lanes = KEYS: scores are computed
+//              transposed so that P^T and dS^T are directly usable as TMEM A-operands)
+//     S^T = K Q_i^T,  dP^T = V dO_i^T
+//     P^T, dS^T in registers (thread = key, columns = queries; lse/delta per column from smem;
+//              the Philox dropout words are exchanged inside lane quads to keep the (query, 4-key) indexing)
+//     dV += P^T dO_i,  dK += dS^T Q_i                      (B operands MN-major); both stay in TMEM
+//
+// TF32 MN-major operands need the 128B_BASE32B smem layout while K-major ones need plain 128B swizzle,
+// so tiles used both ways (K_j in the dq kernel, Q_i / dO_i in the dkdv kernel) are loaded twice by TMA
+// with the two swizzle modes.  Same math as attn_simt.cu (which is the fp32 check for these kernels).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+int pa_attn_delta_launch(const float* o, const float* d_o, int64_t ldo, int B, int H, int Lq, int dh, float* delta, cudaStream_t st);
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct BwdParams {
+  const float* lse; const float* delta; const uint8_t* kpm;
+  float* dq; float* dk; float* dv; int64_t lddq, lddk, lddv;
+  int B, H, Lq, Lk, causal, round_out;
+  float scale, scale_log2;
+  float p_drop; uint64_t seed, offset;
+  int tiles, items;
+};
+
+// ================================================================================================
+//                                           dQ kernel
+// ================================================================================================
+template <int DH> struct CfgQ {
+  static constexpr int BQ = 128, BK = 64, kStages = 3;
+  static constexpr int kChunks = DH / 32;
+  static constexpr int kQBytes = kChunks * BQ * 128;      // Q_i or dO_i (K-major)
+  static constexpr int kKBytes = kChunks * BK * 128;      // one 64-key tile in one layout
+  static constexpr int kStageBytes = 3 * kKBytes;         // K (K-major) | K (MN-major) | V (K-major)
+  static constexpr int kOffQ = 0, kOffDO = kQBytes, kOffKV = 2 * kQBytes;
+  static constexpr int kOffBias = kOffKV + kStages * kStageBytes;
+  static constexpr int kOffBar = kOffBias + 2 * BK * 4;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kColS = 0, kColDP = 128, kColDQ = 256;   // S: 2x64, dP: 2x64, dQ: DH
+  static constexpr int kTmemCols = 512;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_k_mn,
+                      const __grid_constant__ CUtensorMap tm_v, const BwdParams p) {
+  using C = CfgQ<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* qdo_full = bars + 0;  uint64_t* qdo_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;   uint64_t* kv_empty = bars + 5;     // [3] each
+  uint64_t* sdp_full = bars + 8;  uint64_t* ds_full = bars + 10;     // [2] each
+  uint64_t* dq_full = bars + 12;  uint64_t* dq_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_k);
+    tc::tma_prefetch_desc(&tm_k_mn); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(qdo_full, 1); tc::mbar_init(qdo_empty, 1);
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(sdp_full + s, 1); tc::mbar_init(ds_full + s, 4); }
+    tc::mbar_init(dq_full, 1); tc::mbar_init(dq_empty, 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto coords = [&](int item, int& b, int& h, int& q0, int& n) {
+    int qt = item % p.tiles, bh = item / p.tiles;
+    h = bh % p.H; b = bh / p.H; q0 = qt * C::BQ;
+    int all = (p.Lk + C::BK - 1) / C::BK;
+    n = p.causal ? min(all, (q0 + C::BQ - 1) / C::BK + 1) : all;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kc = 0, ic = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, q0, n;
+        coords(item, b, h, q0, n);
+        tc::mbar_wait(qdo_empty, (ic & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(qdo_full, 2 * C::kQBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          tc::tma_load_2d(smem + C::kOffQ + c * (C::BQ * 128), &tm_q, h * DH + c * 32, b * p.Lq + q0, qdo_full);
+          tc::tma_load_2d(smem + C::kOffDO + c * (C::BQ * 128), &tm_do, h * DH + c * 32, b * p.Lq + q0, qdo_full);
+        }
+        for (int j = 0; j < n; ++j, ++kc) {
+          const int s = kc % C::kStages;
+          tc::mbar_wait(kv_empty + s, ((kc / C::kStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(kv_full + s, C::kStageBytes);
+          uint8_t* base = smem + C::kOffKV + s * C::kStageBytes;
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            tc::tma_load_2d(base + c * (C::BK * 128), &tm_k, h * DH + c * 32, b * p.Lk + j * C::BK, kv_full + s);
+            tc::tma_load_2d(base + C::kKBytes + c * (C::BK * 128), &tm_k_mn, h * DH + c * 32, b * p.Lk + j * C::BK, kv_full + s);
+            tc::tma_load_2d(base + 2 * C::kKBytes + c * (C::BK * 128), &tm_v, h * DH + c * 32, b * p.Lk + j * C::BK, kv_full + s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BQ, C::BK, 0, 0);
+      constexpr uint32_t idesc_dq = tc::make_idesc_tf32(C::BQ, DH, 0, 1);
+      uint32_t kc = 0, ic = 0, st = 0, dt = 0;
+      const uint32_t sq = tc::smem_u32(smem + C::kOffQ), sdo = tc::smem_u32(smem + C::kOffDO);
+      auto issue_sdp = [&](uint32_t kcs) {       // S and dP of the tile held in KV stage kcs % kStages
+        const int s = kcs % C::kStages;
+        tc::mbar_wait(kv_full + s, (kcs / C::kStages) & 1);
+        tc::tc_fence_after();
+        const uint32_t sk = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes);
+        const uint32_t sv = sk + 2 * C::kKBytes;
+        const int buf = st & 1;
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint64_t da = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
+          const uint64_t db = tc::make_smem_desc(sk + c * (C::BK * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint64_t da = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
+          const uint64_t db = tc::make_smem_desc(sv + c * (C::BK * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::tc_commit(sdp_full + buf);
+        ++st;
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, q0, n;
+        coords(item, b, h, q0, n);
+        tc::mbar_wait(qdo_full, ic & 1);
+        tc::mbar_wait(dq_empty, (ic & 1) ^ 1);           // previous item's dQ has been read out of TMEM
+        tc::tc_fence_after();
+        issue_sdp(kc);
+        for (int j = 0; j < n; ++j) {
+          if (j + 1 < n) issue_sdp(kc + 1);
+          if (j + 1 == n) tc::tc_commit(qdo_empty);      // all S/dP MMAs of this item are issued
+          const int buf = dt & 1;
+          tc::mbar_wait(ds_full + buf, (dt >> 1) & 1);
+          tc::tc_fence_after();
+          const int s = kc % C::kStages;
+          const uint32_t skm = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes + C::kKBytes);
+          const uint64_t db = tc::make_smem_desc(skm, C::BK * 128, 512, tc::kLayoutSw128Base32);
+#pragma unroll
+          for (int k = 0; k < C::BK / 8; ++k)
+            tc::mma_tf32_ts(tmem_base + C::kColDQ, tmem_base + C::kColS + buf * C::BK + k * 8, tc::desc_advance(db, k * 1024), idesc_dq,
+                            (j > 0 || k > 0) ? 1u : 0u);
+          tc::tc_commit(kv_empty + s);
+          ++kc; ++dt;
+        }
+        tc::tc_commit(dq_full);
+      }
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t thr = drop_threshold(p.p_drop);
+    const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int Lk4 = (p.Lk + 3) / 4;
+    uint32_t sc = 0, ic = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+      int b, h, q0, n;
+      coords(item, b, h, q0, n);
+      const int qi = q0 + row;
+      const bool q_ok = qi < p.Lq;
+      const int64_t rg = ((int64_t)(b * p.H + h) * p.Lq + qi);
+      const float lse = q_ok ? p.lse[rg] : -INFINITY;
+      const float lse2 = lse == -INFINITY ? INFINITY : lse * kLog2e;     // +inf => P = 0
+      const float dl = q_ok ? p.delta[rg] : 0.f;
+      for (int j = 0; j < n; ++j, ++sc) {
+        const int buf = sc & 1, k0 = j * C::BK;
+        if (tid < C::BK) {
+          const int kj = k0 + tid;
+          const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+          bias_s[buf * C::BK + tid] = ok ? 0.f : -INFINITY;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tc::mbar_wait(sdp_full + buf, (sc >> 1) & 1);
+        tc::tc_fence_after();
+        const bool diag = p.causal && (k0 + C::BK - 1 > q0);
+#pragma unroll
+        for (int c0 = 0; c0 < C::BK; c0 += 32) {
+          uint32_t rs[32], rd[32];
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BK + c0, rd);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.p_drop > 0.f) {
+              uint4 rn = philox4x32(p.seed, (uint64_t)(rg * Lk4 + ((k0 + c0 + c) >> 2)), p.offset);
+              mk[0] = rn.x >= thr ? ks : 0.f; mk[1] = rn.y >= thr ? ks : 0.f; mk[2] = rn.z >= thr ? ks : 0.f; mk[3] = rn.w >= thr ? ks : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int kk = c0 + c + e;
+              float v = __uint_as_float(rs[c + e]) * p.scale_log2 + bias_s[buf * C::BK + kk] - lse2;
+              if (diag && k0 + kk > qi) v = -INFINITY;
+              const float pr = exp2f(v);
+              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dl);
+              rs[c + e] = __float_as_uint(tf32_rn(ds));
+            }
+          }
+          tc::tmem_st_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(ds_full + buf);
+      }
+      // dQ_i is complete in TMEM
+      tc::mbar_wait(dq_full, ic & 1);
+      tc::tc_fence_after();
+      float* out = p.dq + ((int64_t)b * p.Lq + qi) * p.lddq + h * DH;
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDQ + c0, r);
+        tc::tmem_ld_wait();
+        if (q_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 v = make_float4(__uint_as_float(r[c]) * p.scale, __uint_as_float(r[c + 1]) * p.scale,
+                                   __uint_as_float(r[c + 2]) * p.scale, __uint_as_float(r[c + 3]) * p.scale);
+            if (p.round_out) v = tf32_rn4(v);
+            *reinterpret_cast<float4*>(out + c0 + c) = v;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(dq_empty);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ================================================================================================
+//                                         dK / dV kernel
+// ================================================================================================
+template <int DH> struct CfgK {
+  static constexpr int BKV = 128, BQ = 64, kStages = 2;
+  static constexpr int kChunks = DH / 32;
+  static constexpr int kKVBytes = kChunks * BKV * 128;    // K_j or V_j (K-major)
+  static constexpr int kQBytes = kChunks * BQ * 128;      // one 64-query tile in one layout
+  static constexpr int kStageBytes = 4 * kQBytes;         // Q K-major | Q MN-major | dO K-major | dO MN-major
+  static constexpr int kOffK = 0, kOffV = kKVBytes, kOffQ = 2 * kKVBytes;
+  static constexpr int kOffStat = kOffQ + kStages * kStageBytes;      // [2 bufs][lse2 | delta][64]
+  static constexpr int kOffBar = kOffStat + 2 * 2 * BQ * 4;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kColS = 0, kColDP = 128, kColDK = 256, kColDV = 256 + DH;
+  static constexpr int kTmemCols = 512;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                        const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_q_mn,
+                        const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_do_mn,
+                        const BwdParams p) {
+  using C = CfgK<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* stat_s = reinterpret_cast<float*>(smem + C::kOffStat);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* kv_full = bars + 0;   uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;    uint64_t* q_empty = bars + 4;      // [2] each
+  uint64_t* st_full = bars + 6;   uint64_t* pds_full = bars + 8;     // [2] each
+  uint64_t* acc_full = bars + 10; uint64_t* acc_empty = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v); tc::tma_prefetch_desc(&tm_q);
+    tc::tma_prefetch_desc(&tm_q_mn); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_do_mn);
+    tc::mbar_init(kv_full, 1); tc::mbar_init(kv_empty, 1);
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(q_full + s, 1); tc::mbar_init(q_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(st_full + s, 1); tc::mbar_init(pds_full + s, 4); }
+    tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int q_tiles_all = (p.Lq + C::BQ - 1) / C::BQ;
+  auto coords = [&](int item, int& b, int& h, int& k0, int& i0) {
+    int kt = item % p.tiles, bh = item / p.tiles;
+    h = bh % p.H; b = bh / p.H; k0 = kt * C::BKV;
+    i0 = p.causal ? k0 / C::BQ : 0;          // first query tile that can see these keys
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t qc = 0, ic = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, k0, i0;
+        coords(item, b, h, k0, i0);
+        tc::mbar_wait(kv_empty, (ic & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(kv_full, 2 * C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          tc::tma_load_2d(smem + C::kOffK + c * (C::BKV * 128), &tm_k, h * DH + c * 32, b * p.Lk + k0, kv_full);
+          tc::tma_load_2d(smem + C::kOffV + c * (C::BKV * 128), &tm_v, h * DH + c * 32, b * p.Lk + k0, kv_full);
+        }
+        for (int i = i0; i < q_tiles_all; ++i, ++qc) {
+          const int s = qc % C::kStages;
+          tc::mbar_wait(q_empty + s, ((qc / C::kStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(q_full + s, C::kStageBytes);
+          uint8_t* base = smem + C::kOffQ + s * C::kStageBytes;
+          const int y = b * p.Lq + i * C::BQ;
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            const int x = h * DH + c * 32, off = c * (C::BQ * 128);
+            tc::tma_load_2d(base + off, &tm_q, x, y, q_full + s);
+            tc::tma_load_2d(base + C::kQBytes + off, &tm_q_mn, x, y, q_full + s);
+            tc::tma_load_2d(base + 2 * C::kQBytes + off, &tm_do, x, y, q_full + s);
+            tc::tma_load_2d(base + 3 * C::kQBytes + off, &tm_do_mn, x, y, q_full + s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BKV, C::BQ, 0, 0);      // [128 keys x 64 queries]
+      constexpr uint32_t idesc_acc = tc::make_idesc_tf32(C::BKV, DH, 0, 1);       // [128 keys x DH]
+      uint32_t qc = 0, ic = 0, st = 0, dt = 0;
+      const uint32_t sk = tc::smem_u32(smem + C::kOffK), sv = tc::smem_u32(smem + C::kOffV);
+      auto issue_st = [&](uint32_t qcs) {
+        const int s = qcs % C::kStages;
+        tc::mbar_wait(q_full + s, (qcs / C::kStages) & 1);
+        tc::tc_fence_after();
+        const uint32_t sq = tc::smem_u32(smem + C::kOffQ + s * C::kStageBytes);
+        const uint32_t sdo = sq + 2 * C::kQBytes;
+        const int buf = st & 1;
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint64_t da = tc::make_smem_desc(sk + c * (C::BKV * 128), 16, 1024);
+          const uint64_t db = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint64_t da = tc::make_smem_desc(sv + c * (C::BKV * 128), 16, 1024);
+          const uint64_t db = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::tc_commit(st_full + buf);
+        ++st;
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        int b, h, k0, i0;
+        coords(item, b, h, k0, i0);
+        const int n = q_tiles_all - i0;
+        tc::mbar_wait(kv_full, ic & 1);
+        tc::mbar_wait(acc_empty, (ic & 1) ^ 1);
+        tc::tc_fence_after();
+        if (n > 0) issue_st(qc);
+        for (int j = 0; j < n; ++j) {
+          if (j + 1 < n) issue_st(qc + 1);
+          if (j + 1 == n) tc::tc_commit(kv_empty);       // K_j / V_j no longer needed once these retire
+          const int buf = dt & 1;
+          tc::mbar_wait(pds_full + buf, (dt >> 1) & 1);
+          tc::tc_fence_after();
+          const int s = qc % C::kStages;
+          const uint32_t sqm = tc::smem_u32(smem + C::kOffQ + s * C::kStageBytes + C::kQBytes);
+          const uint32_t sdom = sqm + 2 * C::kQBytes;
+          const uint64_t dqm = tc::make_smem_desc(sqm, C::BQ * 128, 512, tc::kLayoutSw128Base32);
+          const uint64_t ddom = tc::make_smem_desc(sdom, C::BQ * 128, 512, tc::kLayoutSw128Base32);
+#pragma unroll
+          for (int k = 0; k < C::BQ / 8; ++k)      // dV += P^T dO_i
+            tc::mma_tf32_ts(tmem_base + C::kColDV, tmem_base + C::kColS + buf * C::BQ + k * 8, tc::desc_advance(ddom, k * 1024), idesc_acc,
+                            (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < C::BQ / 8; ++k)      // dK += dS^T Q_i
+            tc::mma_tf32_ts(tmem_base + C::kColDK, tmem_base + C::kColDP + buf * C::BQ + k * 8, tc::desc_advance(dqm, k * 1024), idesc_acc,
+                            (j > 0 || k > 0) ? 1u : 0u);
+          tc::tc_commit(q_empty + s);
+          ++qc; ++dt;
+        }
+        if (n == 0) tc::tc_commit(kv_empty);
+        tc::tc_commit(acc_full);
+      }
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t thr = drop_threshold(p.p_drop);
+    const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int Lk4 = (p.Lk + 3) / 4;
+    const int qlane = lane & 3;                 // position inside the 4-key Philox group
+    uint32_t sc = 0, ic = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+      int b, h, k0, i0;
+      coords(item, b, h, k0, i0);
+      const int kj = k0 + row;
+      const bool k_ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+      const int64_t bh_rows = (int64_t)(b * p.H + h) * p.Lq;
+      const int n = q_tiles_all - i0;
+      for (int j = 0; j < n; ++j, ++sc) {
+        const int buf = sc & 1, q0 = (i0 + j) * C::BQ;
+        {  // per-query statistics of this tile: lse (log2 domain; +inf kills the row) and delta
+          const int q = q0 + (tid & 63);
+          if (tid < 64) {
+            float l = q < p.Lq ? p.lse[bh_rows + q] : -INFINITY;
+            stat_s[buf * 128 + tid] = l == -INFINITY ? INFINITY : l * kLog2e;
+          } else {
+            stat_s[buf * 128 + tid] = q < p.Lq ? p.delta[bh_rows + q] : 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tc::mbar_wait(st_full + buf, (sc >> 1) & 1);
+        tc::tc_fence_after();
+        const bool diag = p.causal && (q0 < k0 + C::BKV - 1);
+        const float* lse2 = stat_s + buf * 128;
+        const float* dl = lse2 + 64;
+#pragma unroll
+        for (int c0 = 0; c0 < C::BQ; c0 += 32) {
+          uint32_t rs[32], rd[32];
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.p_drop > 0.f) {
+              // this lane draws the Philox word of query (q0+c0+c+qlane) for its 4-key group, then the quad
+              // transposes: lane needs component qlane of the words drawn by its 3 neighbours.
+              const int64_t rg = bh_rows + q0 + c0 + c + qlane;
+              uint4 rn = philox4x32(p.seed, (uint64_t)(rg * Lk4 + (kj >> 2)), p.offset);
+              const uint32_t w[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const uint32_t send = w[(qlane - s) & 3];
+                const uint32_t got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((qlane + s) & 3));
+                mk[(qlane + s) & 3] = got >= thr ? ks : 0.f;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int qq = c0 + c + e;
+              float v = __uint_as_float(rs[c + e]) * p.scale_log2 - lse2[qq];
+              if (!k_ok || (diag && kj > q0 + qq)) v = -INFINITY;
+              const float pr = exp2f(v);
+              const float pd = pr * mk[e];
+              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dl[qq]);
+              rs[c + e] = __float_as_uint(tf32_rn(pd));
+              rd[c + e] = __float_as_uint(tf32_rn(ds));
+            }
+          }
+          tc::tmem_st_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
+          tc::tmem_st_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(pds_full + buf);
+      }
+      tc::mbar_wait(acc_full, ic & 1);
+      tc::tc_fence_after();
+      const bool row_ok = kj < p.Lk;
+      float* outk = p.dk + ((int64_t)b * p.Lk + kj) * p.lddk + h * DH;
+      float* outv = p.dv + ((int64_t)b * p.Lk + kj) * p.lddv + h * DH;
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t rk[32], rv[32];
+        tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDK + c0, rk);
+        tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDV + c0, rv);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 a = make_float4(__uint_as_float(rk[c]) * p.scale, __uint_as_float(rk[c + 1]) * p.scale,
+                                   __uint_as_float(rk[c + 2]) * p.scale, __uint_as_float(rk[c + 3]) * p.scale);
+            float4 v = make_float4(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]), __uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3]));
+            if (n == 0) { a = make_float4(0.f, 0.f, 0.f, 0.f); v = a; }
+            if (p.round_out) { a = tf32_rn4(a); v = tf32_rn4(v); }
+            *reinterpret_cast<float4*>(outk + c0 + c) = a;
+            *reinterpret_cast<float4*>(outv + c0 + c) = v;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(acc_empty);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int DH>
+int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
+  int rc = pa_attn_delta_launch(a.o, a.d_o, a.ldo, a.B, a.H, a.Lq, a.dh, a.delta, st);
+  if (rc) return rc;
+  const uint64_t d = (uint64_t)a.H * DH, rq = (uint64_t)a.B * a.Lq, rk = (uint64_t)a.B * a.Lk;
+  BwdParams p{};
+  p.lse = a.lse; p.delta = a.delta; p.kpm = a.kpm;
+  p.dq = a.dq; p.dk = a.dk; p.dv = a.dv; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv;
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.causal = a.causal; p.round_out = a.round_out;
+  p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
+  p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset;
+  {
+    using C = CfgQ<DH>;
+    CUtensorMap tq, tdo, tk, tkm, tv;
+    if ((rc = pa_make_tmap_2d(&tq, a.q, d, rq, (uint64_t)a.ldq * 4, 32, C::BQ))) return rc;
+    if ((rc = pa_make_tmap_2d(&tdo, a.d_o, d, rq, (uint64_t)a.ldo * 4, 32, C::BQ))) return rc;
+    if ((rc = pa_make_tmap_2d(&tk, a.k, d, rk, (uint64_t)a.ldk * 4, 32, C::BK))) return rc;
+    if ((rc = pa_make_tmap_2d(&tkm, a.k, d, rk, (uint64_t)a.ldk * 4, 32, C::BK, true))) return rc;
+    if ((rc = pa_make_tmap_2d(&tv, a.v, d, rk, (uint64_t)a.ldv * 4, 32, C::BK))) return rc;
+    auto kern = attn_bwd_dq_tc_kernel<DH>;
+    static bool done = false;
+    if (!done) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem)); done = true; }
+    p.tiles = (a.Lq + C::BQ - 1) / C::BQ;
+    p.items = p.tiles * a.H * a.B;
+    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, C::kSmem, st>>>(tq, tdo, tk, tkm, tv, p);
+    PA_CHECK_LAUNCH();
+  }
+  {
+    using C = CfgK<DH>;
+    CUtensorMap tk, tv, tq, tqm, tdo, tdom;
+    if ((rc = pa_make_tmap_2d(&tk, a.k, d, rk, (uint64_t)a.ldk * 4, 32, C::BKV))) return rc;
+    if ((rc = pa_make_tmap_2d(&tv, a.v, d, rk, (uint64_t)a.ldv * 4, 32, C::BKV))) return rc;
+    if ((rc = pa_make_tmap_2d(&tq, a.q, d, rq, (uint64_t)a.ldq * 4, 32, C::BQ))) return rc;
+    if ((rc = pa_make_tmap_2d(&tqm, a.q, d, rq, (uint64_t)a.ldq * 4, 32, C::BQ, true))) return rc;
+    if ((rc = pa_make_tmap_2d(&tdo, a.d_o, d, rq, (uint64_t)a.ldo * 4, 32, C::BQ))) return rc;
+    if ((rc = pa_make_tmap_2d(&tdom, a.d_o, d, rq, (uint64_t)a.ldo * 4, 32, C::BQ, true))) return rc;
+    auto kern = attn_bwd_dkdv_tc_kernel<DH>;
+    static bool done = false;
+    if (!done) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem)); done = true; }
+    p.tiles = (a.Lk + C::BKV - 1) / C::BKV;
+    p.items = p.tiles * a.H * a.B;
+    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, C::kSmem, st>>>(tk, tv, tq, tqm, tdo, tdom, p);
+    PA_CHECK_LAUNCH();
+  }
+  return PA_OK;
+}
+
+}  // namespace
+
+int pa_attn_bwd_tc(const pa_attn_bwd_args* a, void* stream) {
+  switch (a->dh) {
+    case 32: return launch<32>(*a, (cudaStream_t)stream);
+    case 64: return launch<64>(*a, (cudaStream_t)stream);
+    default: pa_set_error("pa_attn_bwd (tc): head dim %d unsupported (32, 64)", a->dh); return PA_ERR_UNSUPPORTED;
+  }
+}

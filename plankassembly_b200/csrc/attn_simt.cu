@@ -407,6 +407,14 @@ int launch_bwd(const pa_attn_bwd_args& A, cudaStream_t st) {
 }  // namespace
 
 int pa_attn_fwd_tc(const pa_attn_fwd_args* a, void* stream);  // attn_tc.cu
+int pa_attn_bwd_tc(const pa_attn_bwd_args* a, void* stream);  // attn_bwd_tc.cu
+
+int pa_attn_delta_launch(const float* o, const float* d_o, int64_t ldo, int B, int H, int Lq, int dh, float* delta, cudaStream_t st) {
+  int64_t n = (int64_t)B * Lq * H;
+  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(o, d_o, ldo, B, H, Lq, dh, delta);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -429,6 +437,7 @@ extern "C" int pa_attn_bwd(const pa_attn_bwd_args* a, void* stream) {
   PA_CHECK_ARG(a->ldq % 4 == 0 && a->ldk % 4 == 0 && a->ldv % 4 == 0 && a->ldo % 4 == 0);
   PA_CHECK_ARG(a->lddq % 4 == 0 && a->lddk % 4 == 0 && a->lddv % 4 == 0);
   PA_CHECK_ARG(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o) && aligned16(a->d_o));
+  if (a->impl == 1) return pa_attn_bwd_tc(a, stream);
   PA_CHECK_ARG(a->impl == 0);
   switch (a->dh) {
     case 32: return launch_bwd<32>(*a, (cudaStream_t)stream);

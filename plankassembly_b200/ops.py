@@ -18,6 +18,7 @@ import os
 from ._lib import AttnBwdArgs, AttnFwdArgs, GemmArgs, call
 
 ATTN_IMPL = {'simt': 0, 'tc': 1}
+BWD_TC = os.environ.get('PLANK_B200_ATTN_BWD', 'tc') == 'tc'   # tensor-core backward when the forward was tensor-core
 
 
 def _stream():
@@ -227,7 +228,7 @@ class SelfAttention(Function):
         dqkv = torch.empty_like(qkv)
         base, g = qkv.data_ptr(), dqkv.data_ptr()
         _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
-                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, 0, rnd)
+                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, impl if BWD_TC else 0, rnd)
         return dqkv, None, None, None, None, None, None
 
 
@@ -259,7 +260,7 @@ class CrossAttention(Function):
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         kb, gb = kv.data_ptr(), dkv.data_ptr()
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
-                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, 0, rnd)
+                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, impl if BWD_TC else 0, rnd)
         return dq, dkv, None, None, None, None, None
 
 

@@ -78,8 +78,13 @@ def test_tc_lse_and_backward_pairing():
     ref = attn_ref(q, k, v, None, True, H)
     w = torch.randn(B, L, d, generator=g, dtype=torch.float64)
     (ref * w).sum().backward()
-    out = ops.SelfAttention.apply(qkv, None, H, True, 0.0, 1)
-    (out * w.float().cuda()).sum().backward()
+    ops_bwd = ops.BWD_TC
+    ops.BWD_TC = False                      # pair the tensor-core forward with the fp32 backward kernels
+    try:
+        out = ops.SelfAttention.apply(qkv, None, H, True, 0.0, 1)
+        (out * w.float().cuda()).sum().backward()
+    finally:
+        ops.BWD_TC = ops_bwd
     assert rel_err(out.detach().cpu(), ref.detach()) < TOL
     assert rel_err(qkv.grad.cpu(), q64.grad) < TOL
 
@@ -100,3 +105,79 @@ def test_tc_dropout_matches_simt_mask():
     assert torch.equal(o_tc > 0, o_simt > 0)
     assert abs((o_tc > 0).float().mean().item() - (1 - p)) < 2e-2
     assert rel_err(o_tc.cpu(), o_simt.cpu()) < TOL
+
+
+# ------------------------------------------------------------------------------ backward (tcgen05)
+BWD_TOL = 1e-3     # TF32-rounded P / dS inside the kernels; operands pre-rounded as in the model
+
+
+@pytest.mark.parametrize('B,H,dh,L,causal,tail', CASES)
+def test_self_attention_tc_bwd(B, H, dh, L, causal, tail):
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    d = H * dh
+    qkv = tf32_round(torch.randn(B, L, 3 * d, generator=g)).requires_grad_(True)
+    kpm = torch.zeros(B, L, dtype=torch.bool)
+    if tail:
+        for b in range(B):
+            kpm[b, max(1, L - 1 - 37 * (b + 1)):] = True
+    q64 = qkv.detach().double().cpu().requires_grad_(True)
+    q, k, v = q64.split(d, -1)
+    ref = attn_ref(q, k, v, kpm if tail else None, causal, H)
+    w = tf32_round(torch.randn(B, L, d, generator=g))
+    (ref * w.double().cpu()).sum().backward()
+    ck = kpm.cuda().view(torch.uint8) if tail else None
+    out = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 1)
+    (out * w).sum().backward()
+    torch.cuda.synchronize()
+    gq, gk, gv = qkv.grad.cpu().split(d, -1)
+    rq, rk, rv = q64.grad.split(d, -1)
+    # L = 1: dS = P (dP - delta) is exactly 0 in exact arithmetic, so measure against the scale of dV
+    floor = 1e-4 * rv.abs().max().item()
+    eq, ek, ev = (((a - b).abs().max() / max(b.abs().max().item(), floor)).item() for a, b in ((gq.double(), rq), (gk.double(), rk), (gv.double(), rv)))
+    print(f'B{B} H{H} dh{dh} L{L} causal={causal}: dq {eq:.2e} dk {ek:.2e} dv {ev:.2e}')
+    assert max(eq, ek, ev) < BWD_TOL
+
+
+@pytest.mark.parametrize('B,H,dh,Lq,Lk', [(2, 8, 64, 256, 512), (2, 4, 32, 64, 299), (1, 8, 64, 3, 1199), (2, 4, 32, 128, 5)])
+def test_cross_attention_tc_bwd(B, H, dh, Lq, Lk):
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(22)
+    d = H * dh
+    q = tf32_round(torch.randn(B, Lq, d, generator=g)).requires_grad_(True)
+    kv = tf32_round(torch.randn(B, Lk, 2 * d, generator=g)).requires_grad_(True)
+    kpm = torch.zeros(B, Lk, dtype=torch.bool)
+    for b in range(B):
+        kpm[b, max(1, Lk - 3 - 40 * b):] = True
+    q64 = q.detach().double().cpu().requires_grad_(True)
+    kv64 = kv.detach().double().cpu().requires_grad_(True)
+    k, v = kv64.split(d, -1)
+    ref = attn_ref(q64, k, v, kpm, False, H)
+    w = tf32_round(torch.randn(B, Lq, d, generator=g))
+    (ref * w.double().cpu()).sum().backward()
+    out = ops.CrossAttention.apply(q, kv, kpm.cuda().view(torch.uint8), H, 0.0, 1)
+    (out * w).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(q.grad.cpu(), q64.grad) < BWD_TOL
+    assert rel_err(kv.grad.cpu(), kv64.grad) < BWD_TOL
+
+
+def test_tc_bwd_dropout_matches_fp32_kernels():
+    """Same seed/offset => the tensor-core backward (incl. its quad-transposed Philox words in the
+    key-stationary kernel) must reproduce the fp32 kernels' gradients for the same dropout mask."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    B, H, dh, L, p = 2, 4, 64, 192, 0.2
+    d = H * dh
+    base = tf32_round(torch.randn(B, L, 3 * d, generator=g))
+    w = tf32_round(torch.randn(B, L, d, generator=g))
+    grads = []
+    for impl in (1, 0):
+        qkv = base.clone().requires_grad_(True)
+        ops.RNG.seed, ops.RNG.counter = 99, 7
+        out = ops.SelfAttention.apply(qkv, None, H, True, p, impl)
+        (out * w).sum().backward()
+        grads.append(qkv.grad.clone())
+    torch.cuda.synchronize()
+    for a, b in zip(grads[0].split(d, -1), grads[1].split(d, -1)):
+        assert rel_err(a.cpu(), b.cpu()) < BWD_TOL
