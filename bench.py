@@ -148,6 +148,13 @@ def run_train(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step(resident[i % n_host])
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return {'profiled': 'one step'}
     l0 = _lib.launch_count()
     # --- device-resident timing; the dominant kernel is additionally bracketed with events
     dom_events = []
@@ -238,6 +245,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--dominant', default='pa_attn_bwd', choices=['pa_attn_fwd', 'pa_attn_bwd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-step', action='store_true', help='bracket ONE step with cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
