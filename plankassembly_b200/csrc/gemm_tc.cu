@@ -42,7 +42,7 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 4;           // 16 KB
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
 };
 
@@ -57,6 +57,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -82,8 +83,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int r = tile - b * tiles_per_batch;
     int sp = r / (p.m_tiles * p.n_tiles);
     r -= sp * p.m_tiles * p.n_tiles;
-    nt = r / p.m_tiles;            // m fastest: CTAs running together share the B (weight) tile
-    mt = r - nt * p.m_tiles;
+    mt = r / p.n_tiles;            // n fastest: an activation tile is reused by all its n tiles out of L2
+    nt = r - mt * p.n_tiles;
     kb0 = sp * k_per_split;
     kb1 = min(k_blocks_total, kb0 + k_per_split);
   };
@@ -159,6 +160,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int b, mt, nt, kb0, kb1;
       decode(tile, b, mt, nt, kb0, kb1);
+      // stage this tile's bias slice in smem once (per-element global loads serialised the epilogue)
+      if (p.bias != nullptr) {
+        const int et = threadIdx.x - 64;
+        for (int c = et; c < BN; c += 128) bias_s[acc * BN + c] = (nt * BN + c < p.N) ? __ldg(p.bias + nt * BN + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       tc::mbar_wait(tmem_full + acc, acc_phase);
       tc::tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
@@ -179,7 +186,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float x = __uint_as_float(r[j + e]) * p.alpha;
-              if (p.bias != nullptr && col + e < p.N) x += __ldg(p.bias + col + e);
+              if (p.bias != nullptr) x += bias_s[acc * BN + c0 + j + e];
               if (p.relu) x = fmaxf(x, 0.f);
               v[e] = x;
             }

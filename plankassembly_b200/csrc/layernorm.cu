@@ -138,12 +138,21 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
 }
 
 // dgamma/dbeta += sum over blocks of partial
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * d) return;
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;                 // column of the [2d] (gamma | beta) vector
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * 2 * d + i];
-  if (i < d) dgamma[i] += acc; else dbeta[i - d] += acc;
+  if (i < 2 * d)
+    for (int b = ry; b < nblocks; b += 8) acc += partial[(int64_t)b * 2 * d + i];
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && i < 2 * d) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][cx];
+    if (i < d) dgamma[i] += t; else dbeta[i - d] += t;
+  }
 }
 
 static int ln_grid(int64_t rows) {
@@ -196,7 +205,7 @@ extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, 
   }
 #undef LAUNCH
   PA_CHECK_LAUNCH();
-  ln_param_reduce_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(2 * d + 31) / 32, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
