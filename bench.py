@@ -93,6 +93,7 @@ def run_train(args, rank, world, local_rank):
     import torch.distributed as dist
     from plankassembly_b200 import _lib, synthetic as syn
     from plankassembly_b200.models import build_model
+    from plankassembly_b200.parallel import GradAllReduce
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
@@ -104,9 +105,8 @@ def run_train(args, rank, world, local_rank):
     model = build_model(cfg)
     model.load_state_dict(syn.init_state_dict(cfg))
     model = model.to(dev).train()
-    step_model = model
-    if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    # N > 1: every .grad is a view into one flat buffer -> ONE NCCL all-reduce per step (parallel.py)
+    reducer = GradAllReduce(model.parameters()) if world > 1 else None
     opt = torch.optim.Adam(model.parameters(), lr=cfg.LR, fused=True)
 
     # distinct synthetic drawings per rank (weak scaling: per-GPU batch fixed)
@@ -120,9 +120,14 @@ def run_train(args, rank, world, local_rank):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
 
     def step(batch):
-        opt.zero_grad(set_to_none=True)
-        out = step_model(batch)
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+        out = model(batch)
         out['loss'].backward()
+        if reducer is not None:
+            reducer.sync()
         opt.step()
         return out
 
@@ -203,9 +208,49 @@ def run_train(args, rank, world, local_rank):
                            'frac': ach / pk['tf_sustained'], 'traffic': None, 'peak_source': pk['src'] + ' (sustained bf16)',
                            'avg_launch_ms': avg_ms, 'launches_per_step': calls_per_step,
                            'share_of_step': sum(dom_ms) / ms}
+    if not args.no_decode:
+        res['decode'] = run_decode(model, cfg, host, resident, dev, world, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res['cpu_baseline'] = cpu_baseline_train(sample_batch=2, steps=1)
     return res
+
+
+def run_decode(model, cfg, host, resident, dev, world, timed, reps=2):
+    """BASELINE configs[2]: KV-cached greedy decode, per-GPU batch of drawings, max_len = MAX_OUTPUT_LENGTH.
+    tokens = generated positions (every row decodes until all rows have emitted END, as the reference does)."""
+    from plankassembly_b200 import _lib
+    model.eval()
+    with torch.no_grad():
+        out = model(resident[0])                       # warm-up: buffers, cuBLAS workspaces, CUDA-graph capture
+        n_tok = [0]
+
+        def dec(i):
+            o = model(resident[i % len(resident)])
+            n_tok[0] += o['samples'].numel()
+
+        ms = timed(dec, reps)
+        tok_resident = n_tok[0] * world
+        n_tok[0] = 0
+
+        def dec_e2e(i):
+            hb = host[i % len(host)]
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+            o = model(batch)
+            n_tok[0] += o['samples'].cpu().numel() + o['attach'].cpu().numel() * 0
+
+        ms_e2e = timed(dec_e2e, reps)
+    model.train()
+    B, T = out['samples'].shape
+    d, S, L = cfg.MODEL.NUM_MODEL, cfg.DATA.MAX_INPUT_LENGTH - 1, cfg.MODEL.NUM_DECODER_LAYERS
+    # algorithmic HBM bytes per generated token per sequence (SURVEY 8d): cross K/V + average self K/V, fp32
+    bytes_tok = 2 * L * d * (S + T / 2) * 4
+    gbs = bytes_tok * tok_resident / world / (ms / 1e3) / 1e9
+    pk = peaks()
+    return {'metric': 'greedy-decode generated tokens/sec (KV cache, CUDA-graph step)', 'value': tok_resident / (ms / 1e3),
+            'unit': UNIT, 'ms_per_decode': ms / reps, 'batch_per_gpu': B, 'steps_per_decode': T,
+            'e2e': {'value': n_tok[0] * world / (ms_e2e / 1e3), 'unit': UNIT},
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                         'note': 'algorithmic fp32 K/V bytes per token (cross + mean self cache) / measured time per GPU'}}
 
 
 def cpu_baseline_train(sample_batch, steps):
@@ -245,6 +290,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--dominant', default='pa_attn_bwd', choices=['pa_attn_fwd', 'pa_attn_bwd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-decode', action='store_true')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE step with cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -149,21 +149,24 @@ int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B,
                        float* dists, void* stream);
 
 /* ---- K11/K12: KV-cached greedy decode step pieces (replace the O(T^3) loop models.py:284-307).
- * All state lives in caller-owned device buffers; `t` is the 0-based step. */
-int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, int dof, const float* e_val,
+ * All state lives in caller-owned device buffers; `t` is the 0-based step.  When `t_dev` is not NULL the
+ * step index is read from device memory instead, so that ONE captured CUDA graph replays every step;
+ * pa_decode_advance increments it at the end of a step. */
+int pa_decode_advance(int* t_dev, void* stream);
+int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, const int* t_dev, int dof, const float* e_val,
                     const float* e_coord, const float* e_pos, int d, float* y, void* stream);
 /* Self-attention for the new position: appends k_new/v_new ([B,ld_new]) at slot t of the caches
  * (cache_len rows of stride ld_cache per sequence) and attends over slots 0..len-1 (len = t+1).
  * Cross-attention: pass k_new = NULL, len = S and kpm ([B,len]). */
 int pa_decode_attn(const float* q, int64_t ldq, const float* k_new, const float* v_new, int64_t ld_new,
                    float* k_cache, float* v_cache, int64_t cache_len, int64_t ld_cache, int t, int len,
-                   const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream);
+                   const int* t_dev, const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream);
 /* Heads + eval distribution + sampling for step t (models.py:168-186, 235-256).
  * h [B,d] final-normed hidden (also stored into hfin[:,t,:]); lv [B,V]; pf [B,d]; sw [B].
  * Writes samples[b*ld+t], attach[b*ld+t]; first_end[b] = min(first_end[b], t) when the emitted
  * token is END (the host derives the reference's stop step, models.py:306, as max_b first_end). */
 int pa_decode_head(const float* h, const float* lv, const float* pf, const float* sw, float* hfin,
-                   int64_t Tmax, int B, int d, int V, int t, int end_token, int64_t* samples,
+                   int64_t Tmax, int B, int d, int V, int t, const int* t_dev, int end_token, int64_t* samples,
                    int64_t* attach, int64_t ld, int32_t* first_end, void* stream);
 
 #ifdef __cplusplus

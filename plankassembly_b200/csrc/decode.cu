@@ -11,7 +11,7 @@ constexpr int kThreads = 128;
 template <int DH>
 __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k_new,
                                                                  const float* __restrict__ v_new, int64_t ld_new, float* k_cache,
-                                                                 float* v_cache, int64_t cache_len, int64_t ldc, int t, int len,
+                                                                 float* v_cache, int64_t cache_len, int64_t ldc, int t_host, int len_host, const int* __restrict__ t_dev,
                                                                  const uint8_t* __restrict__ kpm, int H, float scale,
                                                                  float* __restrict__ o) {
   extern __shared__ float s_p[];                // [len] scores -> probabilities
@@ -19,6 +19,9 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
   __shared__ float s_o[kThreads / 32][DH];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = H * DH;
+  // self-attention under a CUDA graph: the step index lives in device memory (len = t + 1)
+  const int t = (t_dev != nullptr && k_new != nullptr) ? *t_dev : t_host;
+  const int len = (t_dev != nullptr && k_new != nullptr) ? t + 1 : len_host;
   float* kc = k_cache + (int64_t)b * cache_len * ldc + h * DH;
   float* vc = v_cache + (int64_t)b * cache_len * ldc + h * DH;
   if (k_new != nullptr) {                       // append this step's key/value (self-attention)
@@ -90,18 +93,26 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
   }
 }
 
+__global__ void decode_advance_kernel(int* t_dev) { *t_dev += 1; }
+
 }  // namespace
+
+extern "C" int pa_decode_advance(int* t_dev, void* stream) {
+  decode_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
 
 extern "C" int pa_decode_attn(const float* q, int64_t ldq, const float* k_new, const float* v_new, int64_t ld_new,
                               float* k_cache, float* v_cache, int64_t cache_len, int64_t ld_cache, int t, int len,
-                              const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream) {
+                              const int* t_dev, const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream) {
   PA_CHECK_ARG(ld_cache % 4 == 0 && B > 0 && H > 0 && len > 0 && len <= cache_len && (k_new == nullptr || (t >= 0 && t < cache_len)));
   dim3 grid(H, B);
-  size_t smem = (size_t)len * sizeof(float);
+  size_t smem = (size_t)(t_dev != nullptr ? cache_len : len) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dh) {
-    case 32: decode_attn_kernel<32><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, kpm, H, scale, o); break;
-    case 64: decode_attn_kernel<64><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, kpm, H, scale, o); break;
+    case 32: decode_attn_kernel<32><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, H, scale, o); break;
+    case 64: decode_attn_kernel<64><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, H, scale, o); break;
     default: pa_set_error("pa_decode_attn: head dim %d unsupported (32, 64)", dh); return PA_ERR_UNSUPPORTED;
   }
   PA_CHECK_LAUNCH();

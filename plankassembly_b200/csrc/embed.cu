@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(128) embed_output_bwd_kernel(const float4* __r
   }
 }
 
-__global__ void __launch_bounds__(128) decode_embed_kernel(const int64_t* __restrict__ samples, int64_t ld, int B, int t, int dof,
+__global__ void __launch_bounds__(128) decode_embed_kernel(const int64_t* __restrict__ samples, int64_t ld, int B, int t_host, const int* __restrict__ t_dev, int dof,
                                                               const float4* __restrict__ e_val, const float4* __restrict__ e_coord,
                                                               const float4* __restrict__ e_pos, int d4, float4* __restrict__ y) {
+  const int t = t_dev != nullptr ? *t_dev : t_host;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * d4) return;
   int c = idx % d4, b = idx / d4;
@@ -177,11 +178,11 @@ extern "C" int pa_embed_output_bwd(const float* dout, const int64_t* value, int6
   return PA_OK;
 }
 
-extern "C" int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, int dof, const float* e_val,
+extern "C" int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, const int* t_dev, int dof, const float* e_val,
                                const float* e_coord, const float* e_pos, int d, float* y, void* stream) {
   PA_CHECK_ARG(B > 0 && t >= 0 && d % 4 == 0);
   int total = B * (d / 4);
-  decode_embed_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(samples, ld, B, t, dof, (const float4*)e_val,
+  decode_embed_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(samples, ld, B, t, t_dev, dof, (const float4*)e_val,
                                                                            (const float4*)e_coord, (const float4*)e_pos, d / 4, (float4*)y);
   PA_CHECK_LAUNCH();
   return PA_OK;

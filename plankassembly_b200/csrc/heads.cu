@@ -193,12 +193,13 @@ __device__ __forceinline__ bool ptr_allowed(int i, int j) {
 
 __global__ void __launch_bounds__(kHeadThreads) decode_head_kernel(const float* __restrict__ h, const float* __restrict__ lv,
                                                                      const float* __restrict__ pf, const float* __restrict__ sw,
-                                                                     float* __restrict__ hfin, int64_t Tmax, int d, int V, int t,
-                                                                     int end_token, int64_t* __restrict__ samples, int64_t* __restrict__ attach,
+                                                                     float* __restrict__ hfin, int64_t Tmax, int d, int V, int t_host,
+                                                                     const int* __restrict__ t_dev, int end_token, int64_t* __restrict__ samples, int64_t* __restrict__ attach,
                                                                      int64_t ld, int32_t* __restrict__ first_end) {
   extern __shared__ float s_lp[];  // [t+1] pointer scores / probs
   __shared__ float redv[kHeadThreads / 32];
   __shared__ int redi[kHeadThreads / 32];
+  const int t = t_dev != nullptr ? *t_dev : t_host;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* hb = h + (int64_t)b * d;
   float* hf = hfin + (int64_t)b * Tmax * d;
@@ -291,11 +292,11 @@ extern "C" int pa_dist_train_full(const float* lv, const float* lp, const float*
 }
 
 extern "C" int pa_decode_head(const float* h, const float* lv, const float* pf, const float* sw, float* hfin,
-                              int64_t Tmax, int B, int d, int V, int t, int end_token, int64_t* samples,
+                              int64_t Tmax, int B, int d, int V, int t, const int* t_dev, int end_token, int64_t* samples,
                               int64_t* attach, int64_t ld, int32_t* first_end, void* stream) {
   PA_CHECK_ARG(B > 0 && d % 4 == 0 && t >= 0 && t < Tmax);
-  decode_head_kernel<<<B, kHeadThreads, (size_t)(t + 1) * sizeof(float), (cudaStream_t)stream>>>(
-      h, lv, pf, sw, hfin, Tmax, d, V, t, end_token, samples, attach, ld, first_end);
+  decode_head_kernel<<<B, kHeadThreads, (size_t)(t_dev != nullptr ? Tmax : t + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      h, lv, pf, sw, hfin, Tmax, d, V, t, t_dev, end_token, samples, attach, ld, first_end);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
