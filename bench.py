@@ -218,7 +218,10 @@ def run_train(args, rank, world, local_rank):
 def run_decode(model, cfg, host, resident, dev, world, timed, reps=2):
     """BASELINE configs[2]: KV-cached greedy decode, per-GPU batch of drawings, max_len = MAX_OUTPUT_LENGTH.
     tokens = generated positions (every row decodes until all rows have emitted END, as the reference does)."""
-    from plankassembly_b200 import _lib
+    from plankassembly_b200 import synthetic as syn
+    # decode with the seeded-init weights (the timed train steps above have moved `model`'s weights; a
+    # half-trained model may emit END everywhere at once, which would stop the loop after one step)
+    model.load_state_dict(syn.init_state_dict(cfg))
     model.eval()
     with torch.no_grad():
         out = model(resident[0])                       # warm-up: buffers, cuBLAS workspaces, CUDA-graph capture
