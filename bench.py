@@ -153,6 +153,17 @@ def run_train(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step(resident[i % n_host])
+    if args.profile_decode:
+        model.load_state_dict(syn.init_state_dict(cfg))
+        model.eval()
+        with torch.no_grad():
+            model(resident[0])
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            model(resident[0])
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return {'profiled': 'one decode'}
     if args.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -294,6 +305,7 @@ def main():
     ap.add_argument('--dominant', default='pa_attn_bwd', choices=['pa_attn_fwd', 'pa_attn_bwd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--profile-decode', action='store_true', help='bracket one greedy decode with cudaProfilerStart/Stop and exit')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE step with cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
