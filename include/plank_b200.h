@@ -78,6 +78,15 @@ int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
  * kpm: [B,Lk] uint8, 1 = PAD key (NULL = none); causal: key j visible to query i iff j <= i.
  * lse: [B,H,Lq] natural-log sum-exp of the masked scaled scores (saved for bwd; may be NULL).
  * impl: 0 = fp32 SIMT (exact mode), 1 = tcgen05 TF32 tensor-core path. */
+/* Attention-probability dropout keep-masks for the tensor-core kernels, generated ONCE per attention call
+ * (all warps of the chip) instead of three times inside the forward / dQ / dK-dV kernels (4 warps per SM):
+ * bit = Philox4x32-10(seed, counter = (bh*Lq + q)*ceil(Lk/4) + k/4, offset)[k%4] >= p*2^32, i.e. exactly the
+ * mask the fp32 kernels derive inline.  rows: [BH, Lq, ceil(Lk/32)] words, bit k%32 of word k/32;
+ * cols: [BH, 32*ceil(Lk/32), ceil(Lq/32)] words, bit q%32 of word q/32 (the key-stationary backward's view). */
+size_t pa_dropout_mask_words(int BH, int Lq, int Lk, int cols);
+int pa_dropout_mask(uint32_t* rows, uint32_t* cols, int BH, int Lq, int Lk, float p_drop, uint64_t seed,
+                    uint64_t offset, void* stream);
+
 typedef struct {
   const float* q; const float* k; const float* v;
   int64_t ldq, ldk, ldv;
@@ -90,6 +99,8 @@ typedef struct {
   float p_drop; uint64_t seed, offset;
   int impl;
   int round_out;               /* write O rounded to TF32 (it feeds a tensor-core GEMM) */
+  const uint32_t* drop_rows;   /* keep-bit masks from pa_dropout_mask (required by impl 1 when p_drop > 0) */
+  const uint32_t* drop_cols;
 } pa_attn_fwd_args;
 int pa_attn_fwd(const pa_attn_fwd_args* args, void* stream);
 
@@ -108,6 +119,8 @@ typedef struct {
   float p_drop; uint64_t seed, offset;
   int impl;
   int round_out;               /* write dq/dk/dv rounded to TF32 */
+  const uint32_t* drop_rows;   /* the masks the forward used */
+  const uint32_t* drop_cols;
 } pa_attn_bwd_args;
 int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
 

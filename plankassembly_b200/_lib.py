@@ -14,7 +14,8 @@ class AttnFwdArgs(C.Structure):
     _fields_ = [('q', vp), ('k', vp), ('v', vp), ('ldq', i64), ('ldk', i64), ('ldv', i64),
                 ('o', vp), ('ldo', i64), ('lse', vp), ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
-                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32)]
+                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32),
+                ('drop_rows', vp), ('drop_cols', vp)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -23,7 +24,8 @@ class AttnBwdArgs(C.Structure):
                 ('dq', vp), ('dk', vp), ('dv', vp), ('lddq', i64), ('lddk', i64), ('lddv', i64),
                 ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
-                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32)]
+                ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32),
+                ('drop_rows', vp), ('drop_cols', vp)]
 
 
 class GemmArgs(C.Structure):
@@ -48,6 +50,8 @@ SIGNATURES = {
     'pa_relu_dropout_fwd': (i32, [vp, i64, f32, u64, u64, vp]),
     'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, i32, vp]),
     'pa_round_tf32': (i32, [vp, vp, i64, vp]),
+    'pa_dropout_mask_words': (sz, [i32, i32, i32, i32]),
+    'pa_dropout_mask': (i32, [vp, vp, i32, i32, i32, f32, u64, u64, vp]),
     'pa_attn_fwd': (i32, [C.POINTER(AttnFwdArgs), vp]),
     'pa_attn_bwd': (i32, [C.POINTER(AttnBwdArgs), vp]),
     'pa_gemm_tf32': (i32, [C.POINTER(GemmArgs), vp]),

@@ -10,7 +10,7 @@
 //              transposed so that P^T and dS^T are directly usable as TMEM A-operands)
 //     S^T = K Q_i^T,  dP^T = V dO_i^T
 //     P^T, dS^T in registers (thread = key, columns = queries; lse/delta per column from smem;
-//              the Philox dropout words are exchanged inside lane quads to keep the (query, 4-key) indexing)
+//              dropout keep-bits come from the column-major bit plane written by dropmask.cu)
 //     dV += P^T dO_i,  dK += dS^T Q_i                      (B operands MN-major); both stay in TMEM
 //
 // TF32 MN-major operands need the 128B_BASE32B smem layout while K-major ones need plain 128B swizzle,
@@ -31,7 +31,7 @@ struct BwdParams {
   float* dq; float* dk; float* dv; int64_t lddq, lddk, lddv;
   int B, H, Lq, Lk, causal, round_out;
   float scale, scale_log2;
-  float p_drop; uint64_t seed, offset;
+  float p_drop; const uint32_t* drop_rows; const uint32_t* drop_cols; int LkW, LqW;
   int tiles, items;
 };
 
@@ -179,9 +179,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int Lk4 = (p.Lk + 3) / 4;
     uint32_t sc = 0, ic = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
       int b, h, q0, n;
@@ -208,14 +206,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BK + c0, rd);
+          uint32_t mw = 0xffffffffu;                       // keep-bits of keys k0+c0 .. +31 for this query row
+          if (p.p_drop > 0.f) mw = (q_ok && ((k0 + c0) >> 5) < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + ((k0 + c0) >> 5)) : 0u;
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            float mk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (p.p_drop > 0.f) {
-              uint4 rn = philox4x32(p.seed, (uint64_t)(rg * Lk4 + ((k0 + c0 + c) >> 2)), p.offset);
-              mk[0] = rn.x >= thr ? ks : 0.f; mk[1] = rn.y >= thr ? ks : 0.f; mk[2] = rn.z >= thr ? ks : 0.f; mk[3] = rn.w >= thr ? ks : 0.f;
-            }
+            float mk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int kk = c0 + c + e;
@@ -418,10 +416,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int Lk4 = (p.Lk + 3) / 4;
-    const int qlane = lane & 3;                 // position inside the 4-key Philox group
     uint32_t sc = 0, ic = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
       int b, h, k0, i0;
@@ -452,23 +447,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
+          uint32_t mw = 0xffffffffu;                       // keep-bits of queries q0+c0 .. +31 for this key (column plane)
+          if (p.p_drop > 0.f)
+            mw = (kj < p.LkW * 32 && ((q0 + c0) >> 5) < p.LqW)
+                     ? __ldg(p.drop_cols + ((int64_t)(b * p.H + h) * (p.LkW * 32) + kj) * p.LqW + ((q0 + c0) >> 5)) : 0u;
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            float mk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (p.p_drop > 0.f) {
-              // this lane draws the Philox word of query (q0+c0+c+qlane) for its 4-key group, then the quad
-              // transposes: lane needs component qlane of the words drawn by its 3 neighbours.
-              const int64_t rg = bh_rows + q0 + c0 + c + qlane;
-              uint4 rn = philox4x32(p.seed, (uint64_t)(rg * Lk4 + (kj >> 2)), p.offset);
-              const uint32_t w[4] = {rn.x, rn.y, rn.z, rn.w};
+            float mk[4];
 #pragma unroll
-              for (int s = 0; s < 4; ++s) {
-                const uint32_t send = w[(qlane - s) & 3];
-                const uint32_t got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((qlane + s) & 3));
-                mk[(qlane + s) & 3] = got >= thr ? ks : 0.f;
-              }
-            }
+            for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int qq = c0 + c + e;
@@ -533,7 +521,12 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.dq = a.dq; p.dk = a.dk; p.dv = a.dv; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv;
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.causal = a.causal; p.round_out = a.round_out;
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
-  p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset;
+  p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols;
+  p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
+  if (a.p_drop > 0.f && (a.drop_rows == nullptr || a.drop_cols == nullptr)) {
+    pa_set_error("pa_attn_bwd (tc): p_drop > 0 needs drop_rows/drop_cols from pa_dropout_mask");
+    return PA_ERR_ARG;
+  }
   {
     using C = CfgQ<DH>;
     CUtensorMap tq, tdo, tk, tkm, tv;

@@ -39,7 +39,7 @@ struct Params {
   float* o; int64_t ldo; float* lse; const uint8_t* kpm;
   int B, H, Lq, Lk, causal, round_out;
   float scale_log2;   // scale * log2(e)
-  float p_drop; uint64_t seed, offset;
+  float p_drop; const uint32_t* drop_rows; int LkW;
   int q_tiles, items;
 };
 
@@ -184,9 +184,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int tid = threadIdx.x - 64;                    // 0..127
-    const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int Lk4 = (p.Lk + 3) / 4;
     uint32_t sc = 0, oc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, q0, n;
@@ -255,12 +253,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         l_run = l_run * corr + rs;
         m_run = m_new;
         if (p.p_drop > 0.f) {
+          // keep-bits of this row's 128 keys: 4 words of the precomputed Philox bit plane (dropmask.cu)
+          uint32_t w[BKV / 32];
 #pragma unroll
-          for (int c = 0; c < BKV; c += 4) {
-            uint4 rn = philox4x32(p.seed, (uint64_t)(row_global * Lk4 + ((k0 + c) >> 2)), p.offset);
-            s[c] = rn.x >= thr ? s[c] * ks : 0.f; s[c + 1] = rn.y >= thr ? s[c + 1] * ks : 0.f;
-            s[c + 2] = rn.z >= thr ? s[c + 2] * ks : 0.f; s[c + 3] = rn.w >= thr ? s[c + 3] * ks : 0.f;
-          }
+          for (int i = 0; i < BKV / 32; ++i)
+            w[i] = (qi < p.Lq && (k0 >> 5) + i < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + (k0 >> 5) + i) : 0u;
+#pragma unroll
+          for (int c = 0; c < BKV; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] * ks : 0.f;
         }
 #pragma unroll
         for (int c0 = 0; c0 < BKV; c0 += 32) {
@@ -311,7 +310,11 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   p.o = a.o; p.ldo = a.ldo; p.lse = a.lse; p.kpm = a.kpm;
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.causal = a.causal; p.round_out = a.round_out;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset;
+  p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.LkW = (a.Lk + 31) / 32;
+  if (a.p_drop > 0.f && a.drop_rows == nullptr) {
+    pa_set_error("pa_attn_fwd (tc): p_drop > 0 needs drop_rows from pa_dropout_mask");
+    return PA_ERR_ARG;
+  }
   p.q_tiles = (a.Lq + BQ - 1) / BQ;
   p.items = p.q_tiles * a.H * a.B;
   auto kern = attn_fwd_tc_kernel<DH>;

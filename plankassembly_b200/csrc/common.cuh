@@ -75,7 +75,7 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
 }
 
 // keep-decision for one element: u32 random >= threshold  (threshold = p * 2^32)
-__device__ __forceinline__ uint32_t drop_threshold(float p) {
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
   return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }

@@ -1,0 +1,59 @@
+// Attention-probability dropout masks as bit planes, generated once per attention call by the whole chip.
+// Inside the tensor-core attention kernels only 4 warps per SM do elementwise work, and Philox4x32-10 was
+// ~2/3 of their instructions (and was recomputed in the forward, dQ and dK/dV kernels).  Here every thread
+// owns (query q, 32 consecutive keys): 8 Philox words -> one row-major mask word; 32 ballots transpose the
+// 32x32 block so that the key-stationary backward can read its (key, 32 queries) word directly.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128) dropout_mask_kernel(uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, int Lq, int Lk,
+                                                            int LkW, int LqW, uint32_t thr, uint64_t seed, uint64_t offset) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kw = blockIdx.x * 4 + warp;            // key word (32 keys)
+  const int qb = blockIdx.y;                       // query block (32 queries)
+  const int bh = blockIdx.z;
+  if (kw >= LkW) return;
+  const int q = qb * 32 + lane;
+  const int Lk4 = (Lk + 3) / 4;
+  uint32_t word = 0;
+  if (q < Lq) {
+    const int64_t rg = (int64_t)bh * Lq + q;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int k4 = kw * 8 + g;
+      if (k4 < Lk4) {
+        uint4 r = philox4x32(seed, (uint64_t)(rg * Lk4 + k4), offset);
+        word |= (uint32_t)(r.x >= thr) << (4 * g) | (uint32_t)(r.y >= thr) << (4 * g + 1) |
+                (uint32_t)(r.z >= thr) << (4 * g + 2) | (uint32_t)(r.w >= thr) << (4 * g + 3);
+      }
+    }
+    rows[rg * LkW + kw] = word;
+  }
+  if (cols != nullptr) {
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t t = __ballot_sync(0xffffffffu, (word >> k) & 1u);   // bit q%32 of key kw*32+k
+      if (lane == k) mine = t;
+    }
+    cols[((int64_t)bh * (LkW * 32) + kw * 32 + lane) * LqW + qb] = mine;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t pa_dropout_mask_words(int BH, int Lq, int Lk, int cols) {
+  const size_t LkW = (Lk + 31) / 32, LqW = (Lq + 31) / 32;
+  return cols ? (size_t)BH * LkW * 32 * LqW : (size_t)BH * Lq * LkW;
+}
+
+extern "C" int pa_dropout_mask(uint32_t* rows, uint32_t* cols, int BH, int Lq, int Lk, float p_drop, uint64_t seed,
+                               uint64_t offset, void* stream) {
+  PA_CHECK_ARG(rows != nullptr && BH > 0 && Lq > 0 && Lk > 0 && p_drop > 0.f && p_drop < 1.f);
+  const int LkW = (Lk + 31) / 32, LqW = (Lq + 31) / 32;
+  dim3 grid((LkW + 3) / 4, LqW, BH);
+  dropout_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rows, cols, Lq, Lk, LkW, LqW, drop_threshold(p_drop), seed, offset);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}

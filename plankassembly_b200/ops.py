@@ -184,20 +184,33 @@ class ReluDropout(Function):
         return g, None
 
 
+def _drop_masks(B, H, Lq, Lk, p_drop, seed, off, device):
+    """Bit planes of the attention-dropout keep mask for the tensor-core kernels (dropmask.cu)."""
+    lib = _lib.load()
+    rows = torch.empty(lib.pa_dropout_mask_words(B * H, Lq, Lk, 0), device=device, dtype=torch.int32)
+    cols = torch.empty(lib.pa_dropout_mask_words(B * H, Lq, Lk, 1), device=device, dtype=torch.int32)
+    call('pa_dropout_mask', rows.data_ptr(), cols.data_ptr(), B * H, Lq, Lk, p_drop, seed, off, _stream())
+    return rows, cols
+
+
 def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, seed, off, impl, want_lse, device, rnd=False):
     o = torch.empty(B, Lq, H * dh, device=device, dtype=torch.float32)
     lse = torch.empty(B, H, Lq, device=device, dtype=torch.float32) if want_lse else None
+    masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, device) if (impl == 1 and p_drop > 0) else (None, None)
     a = AttnFwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), H * dh, _ptr(lse), _ptr(kpm), B, H, Lq, Lk, dh, int(causal),
-                    dh ** -0.5, p_drop, seed, off, impl, int(rnd))
+                    dh ** -0.5, p_drop, seed, off, impl, int(rnd), _ptr(masks[0]), _ptr(masks[1]))
     call('pa_attn_fwd', C.byref(a), _stream())
-    return o, lse
+    return o, lse, masks
 
 
 def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, B, H, Lq, Lk, dh, kpm, causal, p_drop,
-              seed, off, impl, rnd=False):
+              seed, off, impl, rnd=False, masks=(None, None)):
     delta = torch.empty(B, H, Lq, device=o.device, dtype=torch.float32)
+    if impl == 1 and p_drop > 0 and masks[0] is None:
+        masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, o.device)
     a = AttnBwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), do.data_ptr(), H * dh, lse.data_ptr(), delta.data_ptr(),
-                    dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl, int(rnd))
+                    dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl, int(rnd),
+                    _ptr(masks[0]), _ptr(masks[1]))
     call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
 
 
@@ -212,23 +225,23 @@ class SelfAttention(Function):
         d = d3 // 3
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
         base = qkv.data_ptr()
-        o, lse = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
-                           impl, any(ctx.needs_input_grad), qkv.device, rnd)
-        ctx.save_for_backward(qkv, o, lse, kpm)
+        o, lse, masks = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
+                                  impl, any(ctx.needs_input_grad), qkv.device, rnd)
+        ctx.save_for_backward(qkv, o, lse, kpm, *masks)
         ctx.cfg = (H, causal, p_drop, seed, off, impl, rnd)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
-        qkv, o, lse, kpm = ctx.saved_tensors
+        qkv, o, lse, kpm, m_rows, m_cols = ctx.saved_tensors
         H, causal, p_drop, seed, off, impl, rnd = ctx.cfg
         B, L, d3 = qkv.shape
         d = d3 // 3
         dqkv = torch.empty_like(qkv)
         base, g = qkv.data_ptr(), dqkv.data_ptr()
         _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
-                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, impl if BWD_TC else 0, rnd)
+                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, impl if BWD_TC else 0, rnd, (m_rows, m_cols))
         return dqkv, None, None, None, None, None, None
 
 
@@ -244,23 +257,23 @@ class CrossAttention(Function):
         seed, off = RNG.next() if p_drop > 0 else (0, 0)
         kb = kv.data_ptr()
         need = any(ctx.needs_input_grad)
-        o, lse = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
-                           impl, need, q.device, rnd)
-        ctx.save_for_backward(q, kv, o, lse, kpm)
+        o, lse, masks = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
+                                  impl, need, q.device, rnd)
+        ctx.save_for_backward(q, kv, o, lse, kpm, *masks)
         ctx.cfg = (H, p_drop, seed, off, impl, rnd)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
-        q, kv, o, lse, kpm = ctx.saved_tensors
+        q, kv, o, lse, kpm, m_rows, m_cols = ctx.saved_tensors
         H, p_drop, seed, off, impl, rnd = ctx.cfg
         B, Lq, d = q.shape
         Lk = kv.shape[1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         kb, gb = kv.data_ptr(), dkv.data_ptr()
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
-                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, impl if BWD_TC else 0, rnd)
+                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, impl if BWD_TC else 0, rnd, (m_rows, m_cols))
         return dq, dkv, None, None, None, None, None
 
 
