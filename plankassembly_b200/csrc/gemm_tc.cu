@@ -34,6 +34,7 @@ struct GemmParams {
   int relu; float p_drop; uint64_t seed, offset;
   float alpha;
   int round_out;
+  int tma_store;          // epilogue stores through smem + TMA (needs a 16-byte row pitch)
   int m_tiles, n_tiles;
 };
 
@@ -42,27 +43,31 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 4;           // 16 KB
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
+  static constexpr int kStageOut = 4 * 32 * 128;        // per epilogue warp: one 32x32 fp32 tile, 128B-swizzled
+  static constexpr int kSmem = kStages * kStageBytes + kStageOut + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [4 warps][32 rows][128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + C::kStageOut);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);   // [2][BN]
+  float* bias_s = reinterpret_cast<float*>(out_stage + C::kStageOut + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
+    if (p.tma_store) tc::tma_prefetch_desc(&tma_c);
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 4); }
     tc::fence_barrier_init();
@@ -171,13 +176,50 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int row = mt * BM + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       float* crow = p.c + (int64_t)b * p.c_batch_stride + (int64_t)row * p.ldc;
+      uint8_t* my_stage = out_stage + q * (32 * 128);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
         tc::tmem_ld_wait();
         const int col0 = nt * BN + c0;
-        if (row_ok && col0 < p.N) {
+        if (p.tma_store) {
+          if (kb1 > kb0 && col0 < p.N) {        // warp-uniform
+            if (lane == 0) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int col = col0 + j;
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(r[j + e]) * p.alpha;
+                if (p.bias != nullptr) x += bias_s[acc * BN + c0 + j + e];
+                if (p.relu) x = fmaxf(x, 0.f);
+                v[e] = x;
+              }
+              if (p.p_drop > 0.f) {
+                uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col) >> 2), p.offset);
+                v[0] = rn.x >= thr ? v[0] * ks : 0.f; v[1] = rn.y >= thr ? v[1] * ks : 0.f;
+                v[2] = rn.z >= thr ? v[2] * ks : 0.f; v[3] = rn.w >= thr ? v[3] * ks : 0.f;
+              }
+              if (p.round_out) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = tf32_rn(v[e]);
+              }
+              // 128B swizzle: 16-byte chunk index XOR (row & 7) -- the layout the C tensor map expects
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int y = b * p.M + mt * BM + q * 32;
+              if (p.accumulate) tc::tma_reduce_add_2d(&tma_c, my_stage, col0, y);
+              else tc::tma_store_2d(&tma_c, my_stage, col0, y);
+              tc::tma_store_commit();
+            }
+          }
+        } else if (row_ok && col0 < p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int col = col0 + j;
@@ -219,6 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if (p.tma_store && warp >= 2 && lane == 0) tc::tma_store_wait_all();
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -241,7 +284,7 @@ void resolve_encode() {
 template <int BN, bool A_MN, bool B_MN>
 int launch(const pa_gemm_args& a, cudaStream_t st) {
   using C = Cfg<BN>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc_map;
   int rc;
   if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
   else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 4, 32, BK, true);
@@ -256,6 +299,15 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   p.split_k = a.split_k < 1 ? 1 : a.split_k; p.accumulate = a.accumulate;
   p.relu = a.relu; p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset; p.alpha = a.alpha; p.round_out = a.round_out;
   p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
+  // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
+  p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
+                (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));
+  if (p.tma_store) {
+    rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
+    if (rc) return rc;
+  } else {
+    tc_map = ta;
+  }
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -264,7 +316,7 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   }
   int tiles = p.m_tiles * p.n_tiles * p.split_k * p.batch;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, p);
+  kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, tc_map, p);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
@@ -297,7 +349,7 @@ extern "C" int pa_gemm_tf32(const pa_gemm_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool wide = a->N > 128 && (a->N % 256 == 0 || a->N > 1024);
   if (!a->a_mn && !a->b_mn) return wide ? launch<256, false, false>(*a, st) : launch<128, false, false>(*a, st);
-  if (a->a_mn && a->b_mn) return launch<128, true, true>(*a, st);
+  if (a->a_mn && a->b_mn) return (a->N % 256 == 0) ? launch<256, true, true>(*a, st) : launch<128, true, true>(*a, st);
   if (!a->a_mn && a->b_mn) return (a->N % 256 == 0) ? launch<256, false, true>(*a, st) : launch<128, false, true>(*a, st);
   pa_set_error("pa_gemm_tf32: mixed operand majors are not built (a_mn=%d b_mn=%d)", a->a_mn, a->b_mn);
   return PA_ERR_UNSUPPORTED;

@@ -357,7 +357,7 @@ class Linear(Function):
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1]:
             dW = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
-            tiles = ((N + 127) // 128) * ((K + 127) // 128)
+            tiles = ((N + 127) // 128) * ((K + 255) // 256 if K % 256 == 0 else (K + 127) // 128)
             gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
         return dx, dW, db, None, None, None, None, None
