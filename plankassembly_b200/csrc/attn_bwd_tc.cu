@@ -1,5 +1,7 @@
 // Attention backward on the 5th-gen tensor cores (TF32 operands, FP32 accumulation in TMEM).
-// Two persistent, warp-specialised kernels (warp 0 TMA, warp 1 MMA issuer, warps 2..5 elementwise):
+// Two persistent, warp-specialised kernels (warp 0 TMA, warp 1 MMA issuer, warps 2..9 elementwise: two
+// warpgroups, each owning one 32-column half of every 64-column score tile -- warps w and w+4 share a
+// TMEM lane quarter):
 //
 //  dq kernel  (query-stationary, 128 queries x 64-key steps; TMEM lanes = queries)
 //     S  = Q K_j^T,  dP = dO V_j^T                       (tcgen05.mma SS, K-major operands)
@@ -23,7 +25,7 @@ int pa_attn_delta_launch(const float* o, const float* d_o, int64_t ldo, int B, i
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 = two elementwise warpgroups (column halves)
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct BwdParams {
@@ -74,8 +76,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     tc::tma_prefetch_desc(&tm_k_mn); tc::tma_prefetch_desc(&tm_v);
     tc::mbar_init(qdo_full, 1); tc::mbar_init(qdo_empty, 1);
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(sdp_full + s, 1); tc::mbar_init(ds_full + s, 4); }
-    tc::mbar_init(dq_full, 1); tc::mbar_init(dq_empty, 4);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(sdp_full + s, 1); tc::mbar_init(ds_full + s, 8); }
+    tc::mbar_init(dq_full, 1); tc::mbar_init(dq_empty, 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -178,6 +180,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
+    const int half = (warp - 2) >> 2;            // which 32-column half of each tile this warpgroup owns
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     uint32_t sc = 0, ic = 0;
@@ -197,12 +200,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
           bias_s[buf * C::BK + tid] = ok ? 0.f : -INFINITY;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(sdp_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
         const bool diag = p.causal && (k0 + C::BK - 1 > q0);
 #pragma unroll
-        for (int c0 = 0; c0 < C::BK; c0 += 32) {
+        for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 32) {
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BK + c0, rd);
@@ -236,7 +239,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc::tc_fence_after();
       float* out = p.dq + ((int64_t)b * p.Lq + qi) * p.lddq + h * DH;
 #pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
+      for (int c0 = half * 32; c0 < DH; c0 += 64) {
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDQ + c0, r);
         tc::tmem_ld_wait();
@@ -300,8 +303,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     tc::tma_prefetch_desc(&tm_q_mn); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_do_mn);
     tc::mbar_init(kv_full, 1); tc::mbar_init(kv_empty, 1);
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(q_full + s, 1); tc::mbar_init(q_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(st_full + s, 1); tc::mbar_init(pds_full + s, 4); }
-    tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 4);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(st_full + s, 1); tc::mbar_init(pds_full + s, 8); }
+    tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -415,6 +418,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     }
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
+    const int half = (warp - 2) >> 2;            // which 32-column half of each tile this warpgroup owns
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     uint32_t sc = 0, ic = 0;
@@ -432,18 +436,18 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           if (tid < 64) {
             float l = q < p.Lq ? p.lse[bh_rows + q] : -INFINITY;
             stat_s[buf * 128 + tid] = l == -INFINITY ? INFINITY : l * kLog2e;
-          } else {
+          } else if (tid < 128) {
             stat_s[buf * 128 + tid] = q < p.Lq ? p.delta[bh_rows + q] : 0.f;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(st_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
         const bool diag = p.causal && (q0 < k0 + C::BKV - 1);
         const float* lse2 = stat_s + buf * 128;
         const float* dl = lse2 + 64;
 #pragma unroll
-        for (int c0 = 0; c0 < C::BQ; c0 += 32) {
+        for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 32) {
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
@@ -483,7 +487,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       float* outk = p.dk + ((int64_t)b * p.Lk + kj) * p.lddk + h * DH;
       float* outv = p.dv + ((int64_t)b * p.Lk + kj) * p.lddv + h * DH;
 #pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
+      for (int c0 = half * 32; c0 < DH; c0 += 64) {
         uint32_t rk[32], rv[32];
         tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDK + c0, rk);
         tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDV + c0, rv);

@@ -7,8 +7,9 @@
 //   O_j = P V   : tcgen05.mma with A = P straight from TMEM, B = V tile (smem, MN-major, 128B_BASE32B)
 //   O += O_j    : rescaled accumulation in registers (no TMEM read-modify-write of O)
 //
-// Persistent CTAs (one per SM), 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = softmax/accumulate warpgroup (128 threads = 128 query rows = 128 TMEM lanes).
+// Persistent CTAs (one per SM), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = two softmax/accumulate warpgroups (each: 128 threads = 128 query rows = 128 TMEM lanes,
+// owning one half of the key columns of every tile and one half of the head-dim columns of O).
 // Pipelines: K ring (3 stages) and V ring (2 stages) fed by TMA; S/P and O double-buffered in TMEM so
 // QK^T of tile j+1 and P V of tile j overlap the softmax of tile j.
 //   Reference: torch nn/functional.py multi_head_attention_forward as reached from ref models.py:206,212.
@@ -18,7 +19,7 @@
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two warpgroups)
 constexpr int kKStages = 3, kVStages = 2;
 
 template <int DH> struct Cfg {
@@ -28,7 +29,8 @@ template <int DH> struct Cfg {
   static constexpr int kOffK = kTileBytes;
   static constexpr int kOffV = kOffK + kKStages * kTileBytes;
   static constexpr int kOffBias = kOffV + kVStages * kTileBytes;
-  static constexpr int kOffBar = kOffBias + 2 * BKV * 4;
+  static constexpr int kOffXch = kOffBias + 2 * BKV * 4;     // [2 bufs x 2 halves + 2][128] floats: max / sum exchange
+  static constexpr int kOffBar = kOffXch + 6 * BQ * 4;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColS = 0;                          // 2 x 128 columns  S / P
@@ -51,6 +53,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
+  float* xch_s = reinterpret_cast<float*>(smem + C::kOffXch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
@@ -71,8 +74,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int s = 0; s < kKStages; ++s) { tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1); }
     for (int s = 0; s < kVStages; ++s) { tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 1); }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 4);
-      tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 4);
+      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 8);
+      tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 8);
     }
     tc::fence_barrier_init();
   }
@@ -179,12 +182,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else {
-    // ================================ softmax / accumulate warpgroup ================================
+    // ============================ softmax / accumulate: two warpgroups ============================
+    // Warps 2..5 and 6..9 share TMEM lane quarters pairwise; warpgroup `half` owns key columns
+    // [64*half, 64*half+64) of every 128-key tile and head-dim columns [32*half, 32*half+32) of O.
+    // Row maxima are exchanged through smem once per tile; each half keeps a partial row sum.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int tid = threadIdx.x - 64;                    // 0..127
+    const int tid = threadIdx.x - 64;                    // 0..255
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    constexpr int HC = BKV / 2;                          // score columns per half
+    const bool has_o = half * 32 < DH;
     uint32_t sc = 0, oc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, q0, n;
@@ -192,21 +201,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int qi = q0 + row;
       const int64_t row_global = ((int64_t)(b * p.H + h) * p.Lq + qi);
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-      float o_acc[DH];
+      float o_acc[32];
 #pragma unroll
-      for (int c = 0; c < DH; ++c) o_acc[c] = 0.f;
+      for (int c = 0; c < 32; ++c) o_acc[c] = 0.f;
 
       auto accumulate_o = [&]() {
         const int obuf = oc & 1;
         tc::mbar_wait(o_full + obuf, (oc >> 1) & 1);
         tc::tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
+        if (has_o) {
           uint32_t r[32];
-          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColO + obuf * DH + c0, r);
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColO + obuf * DH + half * 32, r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o_acc[c0 + c] = o_acc[c0 + c] * corr_prev + __uint_as_float(r[c]);
+          for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_prev + __uint_as_float(r[c]);
         }
         tc::tc_fence_before();
         __syncwarp();
@@ -217,18 +225,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < n; ++j) {
         const int buf = sc & 1;
         const int k0 = j * BKV;
-        {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
+        if (tid < BKV) {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
           const int kj = k0 + tid;
           const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
           bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(s_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
-        const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV;
-        float s[BKV];
+        const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + half * HC;
+        float s[HC];
 #pragma unroll
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
+        for (int c0 = 0; c0 < HC; c0 += 32) {
           uint32_t r[32];
           tc::tmem_ld_32x32(s_addr + c0, r);
           tc::tmem_ld_wait();
@@ -238,31 +246,36 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < BKV; ++c) {
-          float v = s[c] * p.scale_log2 + bias_s[buf * BKV + c];
-          if (diag && k0 + c > qi) v = -INFINITY;
+        for (int c = 0; c < HC; ++c) {
+          float v = s[c] * p.scale_log2 + bias_s[buf * BKV + half * HC + c];
+          if (diag && k0 + half * HC + c > qi) v = -INFINITY;
           s[c] = v;
           mx = fmaxf(mx, v);
         }
+        xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
         const float m_new = fmaxf(m_run, mx);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float corr = exp2f(m_run - m_safe);
         float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < BKV; ++c) { s[c] = exp2f(s[c] - m_safe); rs += s[c]; }
-        l_run = l_run * corr + rs;
+        for (int c = 0; c < HC; ++c) { s[c] = exp2f(s[c] - m_safe); rs += s[c]; }
+        l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
-          // keep-bits of this row's 128 keys: 4 words of the precomputed Philox bit plane (dropmask.cu)
-          uint32_t w[BKV / 32];
+          // keep-bits of this row's 64 keys: 2 words of the precomputed Philox bit plane (dropmask.cu)
+          uint32_t w[HC / 32];
 #pragma unroll
-          for (int i = 0; i < BKV / 32; ++i)
-            w[i] = (qi < p.Lq && (k0 >> 5) + i < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + (k0 >> 5) + i) : 0u;
+          for (int i = 0; i < HC / 32; ++i) {
+            const int wi = ((k0 + half * HC) >> 5) + i;
+            w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
+          }
 #pragma unroll
-          for (int c = 0; c < BKV; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] * ks : 0.f;
+          for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] * ks : 0.f;
         }
 #pragma unroll
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
+        for (int c0 = 0; c0 < HC; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(tf32_rn(s[c0 + c]));
@@ -277,18 +290,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         corr_prev = corr;
       }
       accumulate_o();
+      // total row sum = sum of the two halves' partial sums
+      xch_s[(4 + half) * BQ + row] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float l_tot = l_run + xch_s[(4 + (half ^ 1)) * BQ + row];
       if (qi < p.Lq) {
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH;
+        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        if (has_o) {
+          float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + half * 32;
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-          float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-          if (p.round_out) v = tf32_rn4(v);
-          *reinterpret_cast<float4*>(op + c) = v;
+          for (int c = 0; c < 32; c += 4) {
+            float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+            if (p.round_out) v = tf32_rn4(v);
+            *reinterpret_cast<float4*>(op + c) = v;
+          }
         }
-        if (p.lse != nullptr)
-          p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+        if (p.lse != nullptr && half == 0)
+          p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
     }
   }
   tc::tc_fence_before();
