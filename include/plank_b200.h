@@ -53,9 +53,11 @@ int pa_embed_output_bwd(const float* dout, const int64_t* value, int64_t ld, int
 /* ---- K6/K7: y = LayerNorm_eps(x + dropout_p(a)) -- the post-norm residual blocks of
  * torch nn/modules/transformer.py (encoder :952-956, decoder :1144-1153) as configured by
  * models.py:60-69 (eps = 1.0 in layers, 1e-5 in the two final norms).  a may be NULL
- * (final norms).  s receives the pre-norm sum (saved for bwd; may alias nothing, may be NULL
+ * (final norms).  a_bias (may be NULL) is the bias of the linear that produced `a`, folded in here so
+ * that its gradient (column sums of da -> d_a_bias, accumulated +=) comes out of the backward kernel for free.
+ * s receives the pre-norm sum (saved for bwd; may alias nothing, may be NULL
  * in inference); stats = [rows,2] (mean, rstd), may be NULL in inference. */
-int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
+int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias, const float* gamma, const float* beta, float eps,
                   float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
                   float* stats, void* stream);
 /* dx = grad wrt x (and wrt s); da = dropout-masked copy (may be NULL); dgamma/dbeta are
@@ -63,11 +65,14 @@ int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const floa
 size_t pa_add_ln_bwd_workspace(int64_t rows, int d);
 int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma,
                   float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da,
-                  int round_da, float* dgamma, float* dbeta, void* partial, void* stream);
+                  int round_da, float* dgamma, float* dbeta, float* d_a_bias, void* partial, void* stream);
 
 /* ---- FFN activation: z <- dropout_p(relu(z)) in place (transformer.py _ff_block). */
 int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t seed, uint64_t offset, void* stream);
 int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float p_drop, int round_tf32, void* stream);
+/* same on a [rows, N] gradient, also accumulating its column sums into dbias[N] (the linear's bias gradient) */
+int pa_relu_dropout_bwd_colsum(const float* out, float* g, int64_t rows, int N, float p_drop, int round_tf32,
+                               float* dbias, void* stream);
 /* dst = round-to-nearest-TF32(src): shadow copies of the weights for the tensor-core path. */
 int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 /* x <- dropout_p(x) in place (sub-block output dropouts are fused into pa_add_ln_*). */
@@ -121,6 +126,7 @@ typedef struct {
   int round_out;               /* write dq/dk/dv rounded to TF32 */
   const uint32_t* drop_rows;   /* the masks the forward used */
   const uint32_t* drop_cols;
+  float* dbias;                /* impl 1 only, may be NULL: [3*H*dh] += column sums of (dq | dk | dv) = in-proj bias gradient */
 } pa_attn_bwd_args;
 int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
 

@@ -25,7 +25,7 @@ class AttnBwdArgs(C.Structure):
                 ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
                 ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32),
-                ('drop_rows', vp), ('drop_cols', vp)]
+                ('drop_rows', vp), ('drop_cols', vp), ('dbias', vp)]
 
 
 class GemmArgs(C.Structure):
@@ -44,11 +44,12 @@ SIGNATURES = {
     'pa_embed_input_bwd': (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), i32, i64, i32, vp]),
     'pa_embed_output_fwd': (i32, [vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     'pa_embed_output_bwd': (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp]),
-    'pa_add_ln_fwd': (i32, [vp, vp, vp, vp, f32, f32, u64, u64, i64, i32, vp, vp, vp, vp, vp]),
+    'pa_add_ln_fwd': (i32, [vp, vp, vp, vp, vp, f32, f32, u64, u64, i64, i32, vp, vp, vp, vp, vp]),
     'pa_add_ln_bwd_workspace': (sz, [i64, i32]),
-    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
+    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
     'pa_relu_dropout_fwd': (i32, [vp, i64, f32, u64, u64, vp]),
     'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, i32, vp]),
+    'pa_relu_dropout_bwd_colsum': (i32, [vp, vp, i64, i32, f32, i32, vp, vp]),
     'pa_round_tf32': (i32, [vp, vp, i64, vp]),
     'pa_dropout_mask_words': (sz, [i32, i32, i32, i32]),
     'pa_dropout_mask': (i32, [vp, vp, i32, i32, i32, f32, u64, u64, vp]),

@@ -34,6 +34,7 @@ struct BwdParams {
   int B, H, Lq, Lk, causal, round_out;
   float scale, scale_log2;
   float p_drop; const uint32_t* drop_rows; const uint32_t* drop_cols; int LkW, LqW;
+  float* dbias;          // [3*H*DH] += column sums of dq | dk | dv (in-projection bias gradient), may be NULL
   int tiles, items;
 };
 
@@ -251,6 +252,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (p.round_out) v = tf32_rn4(v);
             *reinterpret_cast<float4*>(out + c0 + c) = v;
           }
+        }
+        if (p.dbias != nullptr) {          // q-bias gradient: column sums over this warp's 32 query rows
+          float cs[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) cs[c] = q_ok ? __uint_as_float(r[c]) * p.scale : 0.f;
+          const float t = warp_colsum32(cs, lane);
+          atomicAdd(p.dbias + h * DH + c0 + lane, t);
         }
       }
       tc::tc_fence_before();
@@ -504,6 +512,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             *reinterpret_cast<float4*>(outv + c0 + c) = v;
           }
         }
+        if (p.dbias != nullptr) {          // k- and v-bias gradients: column sums over this warp's 32 key rows
+          float ck[32], cv[32];
+          const bool use = row_ok && n > 0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { ck[c] = use ? __uint_as_float(rk[c]) * p.scale : 0.f; cv[c] = use ? __uint_as_float(rv[c]) : 0.f; }
+          const float tk = warp_colsum32(ck, lane), tv = warp_colsum32(cv, lane);
+          const int dmodel = p.H * DH;
+          atomicAdd(p.dbias + dmodel + h * DH + c0 + lane, tk);
+          atomicAdd(p.dbias + 2 * dmodel + h * DH + c0 + lane, tv);
+        }
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -525,7 +543,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.dq = a.dq; p.dk = a.dk; p.dv = a.dv; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv;
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.causal = a.causal; p.round_out = a.round_out;
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
-  p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols;
+  p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols; p.dbias = a.dbias;
   p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
   if (a.p_drop > 0.f && (a.drop_rows == nullptr || a.drop_cols == nullptr)) {
     pa_set_error("pa_attn_bwd (tc): p_drop > 0 needs drop_rows/drop_cols from pa_dropout_mask");

@@ -11,7 +11,7 @@ constexpr int kLnWarps = 4;
 constexpr int kLnMaxBlocks = kNumSMs * 4;
 
 template <int NV>  // float4 per lane; d = NV*128
-__global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a,
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ abias,
                                                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float eps, float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
                                                                      float4* __restrict__ y, float4* __restrict__ y_r, float4* __restrict__ s_out, float2* __restrict__ stats) {
@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
       v[i] = __ldg(x + row * d4 + c);
       if (a != nullptr) {
         float4 av = __ldg(a + row * d4 + c);
+        if (abias != nullptr) {           // bias of the linear that produced `a` (its GEMM ran bias-free)
+          float4 bb = __ldg(abias + c);
+          av.x += bb.x; av.y += bb.y; av.z += bb.z; av.w += bb.w;
+        }
         if (p_drop > 0.f) {
           uint4 r = philox4x32(seed, (uint64_t)(row * d4 + c), offset);
           av.x = r.x >= thr ? av.x * keep_scale : 0.f;
@@ -68,15 +72,15 @@ template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
                                                                      const float2* __restrict__ stats, const float4* __restrict__ gamma,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
-                                                                     float4* __restrict__ dx, float4* __restrict__ da, int round_da, float* __restrict__ partial) {
+                                                                     float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32, d = NV * 128;
   const float inv_d = 1.f / (float)d;
   const uint32_t thr = drop_threshold(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], dab[NV];      // dab: column sums of da = gradient of the folded linear bias
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = dab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
     const float2 st = __ldg(stats + row);
     float4 g[NV], xh[NV];
@@ -116,16 +120,17 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
           o.w = r.w >= thr ? o.w * keep_scale : 0.f;
         }
         da[row * d4 + c] = round_da ? tf32_rn4(o) : o;
+        if (want_dabias) { dab[i].x += o.x; dab[i].y += o.y; dab[i].z += o.z; dab[i].w += o.w; }
       }
     }
   }
-  // block reduce the per-warp gamma/beta partials -> partial[block][2][d]
-  __shared__ float4 sm[kLnWarps][2][NV * 32];
+  // block reduce the per-warp gamma/beta/(bias) partials -> partial[block][3][d]
+  __shared__ float4 sm[kLnWarps][3][NV * 32];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { sm[warp][0][lane + i * 32] = dg[i]; sm[warp][1][lane + i * 32] = db[i]; }
+  for (int i = 0; i < NV; ++i) { sm[warp][0][lane + i * 32] = dg[i]; sm[warp][1][lane + i * 32] = db[i]; sm[warp][2][lane + i * 32] = dab[i]; }
   __syncthreads();
-  float4* out = reinterpret_cast<float4*>(partial) + (int64_t)blockIdx.x * 2 * d4;
-  for (int i = threadIdx.x; i < 2 * d4; i += blockDim.x) {
+  float4* out = reinterpret_cast<float4*>(partial) + (int64_t)blockIdx.x * 3 * d4;
+  for (int i = threadIdx.x; i < 3 * d4; i += blockDim.x) {
     int which = i / d4, c = i % d4;
     float4 acc = sm[0][which][c];
 #pragma unroll
@@ -138,20 +143,21 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
 }
 
 // dgamma/dbeta += sum over blocks of partial
-__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta) {
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta, float* dabias) {
   __shared__ float sm[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + cx;                 // column of the [2d] (gamma | beta) vector
+  const int i = blockIdx.x * 32 + cx;                 // column of the [3d] (gamma | beta | linear bias) vector
+  const int ncol = dabias != nullptr ? 3 * d : 2 * d;
   float acc = 0.f;
-  if (i < 2 * d)
-    for (int b = ry; b < nblocks; b += 8) acc += partial[(int64_t)b * 2 * d + i];
+  if (i < ncol)
+    for (int b = ry; b < nblocks; b += 8) acc += partial[(int64_t)b * 3 * d + i];
   sm[ry][cx] = acc;
   __syncthreads();
-  if (ry == 0 && i < 2 * d) {
+  if (ry == 0 && i < ncol) {
     float t = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; ++r) t += sm[r][cx];
-    if (i < d) dgamma[i] += t; else dbeta[i - d] += t;
+    if (i < d) dgamma[i] += t; else if (i < 2 * d) dbeta[i - d] += t; else dabias[i - 2 * d] += t;
   }
 }
 
@@ -160,9 +166,9 @@ static int ln_grid(int64_t rows) {
   return (int)(nb < kLnMaxBlocks ? nb : kLnMaxBlocks);
 }
 
-extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 2 * d * sizeof(float); }
+extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 3 * d * sizeof(float); }
 
-extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma, const float* beta, float eps,
+extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias, const float* gamma, const float* beta, float eps,
                              float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
                              float* stats, void* stream) {
   PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && p_drop >= 0.f && p_drop < 1.f);
@@ -170,7 +176,7 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma,
   int grid = ln_grid(rows);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
-  add_ln_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)x, (const float4*)a, (const float4*)gamma,     \
+  add_ln_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)x, (const float4*)a, (const float4*)a_bias, (const float4*)gamma, \
                                                          (const float4*)beta, eps, p_drop, seed, offset, rows,          \
                                                          (float4*)y, (float4*)y_tf32, (float4*)s, (float2*)stats)
   switch (d / 128) {
@@ -187,15 +193,15 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* gamma,
 
 extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma, float p_drop,
                              uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, int round_da, float* dgamma,
-                             float* dbeta, void* partial, void* stream) {
-  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr);
+                             float* dbeta, float* d_a_bias, void* partial, void* stream) {
+  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr && !(d_a_bias != nullptr && da == nullptr));
   if (rows == 0) return PA_OK;
   int grid = ln_grid(rows);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
   add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)dy2, (const float4*)s, (const float2*)stats,    \
                                                          (const float4*)gamma, p_drop, seed, offset, rows, (float4*)dx, \
-                                                         (float4*)da, round_da, (float*)partial)
+                                                         (float4*)da, round_da, d_a_bias != nullptr, (float*)partial)
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -205,7 +211,7 @@ extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, 
   }
 #undef LAUNCH
   PA_CHECK_LAUNCH();
-  ln_param_reduce_kernel<<<(2 * d + 31) / 32, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta, d_a_bias);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
@@ -241,6 +247,36 @@ extern "C" int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t s
   int64_t n4 = n / 4;
   int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
   relu_dropout_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)z, n4, p_drop, seed, offset);
+  PA_CHECK_LAUNCH();
+  return PA_OK;
+}
+
+// Same as relu_dropout_bwd_kernel for a [rows, N] gradient, plus its column sums (= bias gradient of the
+// linear that produced the activation): a thread keeps one float4 column group, blocks stride over rows.
+__global__ void __launch_bounds__(256) relu_dropout_bwd_colsum_kernel(const float4* __restrict__ out, float4* __restrict__ g, int64_t rows, int cols4,
+                                                                        float ks, int round_out, float* __restrict__ dbias) {
+  const int c = threadIdx.x % cols4, r_in = threadIdx.x / cols4, rpi = blockDim.x / cols4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * rpi + r_in; r < rows; r += (int64_t)gridDim.x * rpi) {
+    const int64_t i = r * cols4 + c;
+    float4 o = __ldg(out + i), v = g[i];
+    v.x = o.x > 0.f ? v.x * ks : 0.f; v.y = o.y > 0.f ? v.y * ks : 0.f;
+    v.z = o.z > 0.f ? v.z * ks : 0.f; v.w = o.w > 0.f ? v.w * ks : 0.f;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    g[i] = round_out ? tf32_rn4(v) : v;
+  }
+  atomicAdd(reinterpret_cast<float4*>(dbias) + c, acc);
+}
+
+extern "C" int pa_relu_dropout_bwd_colsum(const float* out, float* g, int64_t rows, int N, float p_drop, int round_tf32,
+                                          float* dbias, void* stream) {
+  PA_CHECK_ARG(rows >= 0 && N % 4 == 0 && N / 4 <= 256 && 256 % (N / 4) == 0 && dbias != nullptr && p_drop >= 0.f && p_drop < 1.f);
+  if (rows == 0) return PA_OK;
+  const int cols4 = N / 4, rpi = 256 / cols4;
+  int64_t nb = (rows + rpi - 1) / rpi;
+  int grid = (int)(nb < kNumSMs * 4 ? nb : kNumSMs * 4);
+  relu_dropout_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, rows, cols4,
+                                                                          p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, round_tf32, dbias);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

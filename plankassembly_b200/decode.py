@@ -63,7 +63,7 @@ class GreedyDecoder:
         self._key, self.graph = key, None
 
     def _add_ln(self, x, a, norm, eps, out):
-        call('pa_add_ln_fwd', x.data_ptr(), a.data_ptr() if a is not None else None, norm.weight.data_ptr(),
+        call('pa_add_ln_fwd', x.data_ptr(), a.data_ptr() if a is not None else None, None, norm.weight.data_ptr(),
              norm.bias.data_ptr(), eps, 0.0, 0, 0, x.shape[0], x.shape[1], out.data_ptr(), None, None, None, _stream())
         return out
 

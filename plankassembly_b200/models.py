@@ -149,26 +149,28 @@ class PlankModel(nn.Module):
         return ops.EmbedOutput.apply(output_value, T, self.num_output_dof, want_r, self.input_embeddings['input_value'].weight,
                                      self.query_coord_embedding.weight, self.query_pos_embedding.weight)
 
-    def _add_ln(self, x, a, norm, eps, p, tf):
-        """-> (y, y_r): y_r is the TF32-rounded copy for the next GEMM (y itself in exact mode)."""
+    def _add_ln(self, x, a, norm, eps, p, tf, a_bias=None):
+        """-> (y, y_r): y_r is the TF32-rounded copy for the next GEMM (y itself in exact mode).
+        a_bias: bias of the linear that produced `a` when that GEMM ran bias-free (TF32 path)."""
         if tf:
-            return ops.AddLayerNorm.apply(x, a, norm.weight, norm.bias, eps, p, True, a is not None)
-        y = ops.AddLayerNorm.apply(x, a, norm.weight, norm.bias, eps, p, False, False)
+            return ops.AddLayerNorm.apply(x, a, a_bias, norm.weight, norm.bias, eps, p, True, a is not None)
+        y = ops.AddLayerNorm.apply(x, a, None, norm.weight, norm.bias, eps, p, False, False)
         return y, y
 
     def _ffn(self, layer, x_r, tf):
         h = ops.linear(x_r, layer.linear1.weight, layer.linear1.bias, relu=True, p_drop=self._p(), tf32=tf, round_out=True)
-        return ops.linear(h, layer.linear2.weight, layer.linear2.bias, tf32=tf, round_dx=True)
+        # TF32 path: linear2 runs bias-free, its bias is folded into the following residual+LayerNorm kernel
+        return ops.linear(h, layer.linear2.weight, None if tf else layer.linear2.bias, tf32=tf, round_dx=True)
 
     def _encode(self, x, x_r, in_kpm):
         p, H, tf = self._p(), self.num_head, self._tf32()
         for layer in self.encoder.layers:
             sa = layer.self_attn
-            qkv = ops.linear(x_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True)
-            a = ops.SelfAttention.apply(qkv, in_kpm, H, False, p, self._impl(), tf)
-            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, tf32=tf, round_dx=True)
-            x, x_r = self._add_ln(x, a, layer.norm1, self.layer_eps, p, tf)
-            x, x_r = self._add_ln(x, self._ffn(layer, x_r, tf), layer.norm2, self.layer_eps, p, tf)
+            qkv = ops.linear(x_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True, bias_grad=False)
+            a = ops.SelfAttention.apply(qkv, sa.in_proj_bias if tf else None, in_kpm, H, False, p, self._impl(), tf)
+            a = ops.linear(a, sa.out_proj.weight, None if tf else sa.out_proj.bias, tf32=tf, round_dx=True)
+            x, x_r = self._add_ln(x, a, layer.norm1, self.layer_eps, p, tf, sa.out_proj.bias)
+            x, x_r = self._add_ln(x, self._ffn(layer, x_r, tf), layer.norm2, self.layer_eps, p, tf, layer.linear2.bias)
         if self.encoder.norm is not None:
             x, x_r = self._add_ln(x, None, self.encoder.norm, 1e-5, 0.0, tf)
         return x, x_r
@@ -177,16 +179,16 @@ class PlankModel(nn.Module):
         p, H, d, tf = self._p(), self.num_head, self.num_model, self._tf32()
         for layer in self.decoder.layers:
             sa, ca = layer.self_attn, layer.multihead_attn
-            qkv = ops.linear(y_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True)
-            a = ops.SelfAttention.apply(qkv, out_kpm, H, True, p, self._impl(), tf)
-            a = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, tf32=tf, round_dx=True)
-            y, y_r = self._add_ln(y, a, layer.norm1, self.layer_eps, p, tf)
-            q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True)
-            kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True)
-            a = ops.CrossAttention.apply(q, kv, in_kpm, H, p, self._impl(), tf)
-            a = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias, tf32=tf, round_dx=True)
-            y, y_r = self._add_ln(y, a, layer.norm2, self.layer_eps, p, tf)
-            y, y_r = self._add_ln(y, self._ffn(layer, y_r, tf), layer.norm3, self.layer_eps, p, tf)
+            qkv = ops.linear(y_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True, bias_grad=False)
+            a = ops.SelfAttention.apply(qkv, sa.in_proj_bias if tf else None, out_kpm, H, True, p, self._impl(), tf)
+            a = ops.linear(a, sa.out_proj.weight, None if tf else sa.out_proj.bias, tf32=tf, round_dx=True)
+            y, y_r = self._add_ln(y, a, layer.norm1, self.layer_eps, p, tf, sa.out_proj.bias)
+            q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True, bias_grad=False)
+            kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True, bias_grad=False)
+            a = ops.CrossAttention.apply(q, kv, ca.in_proj_bias if tf else None, in_kpm, H, p, self._impl(), tf)
+            a = ops.linear(a, ca.out_proj.weight, None if tf else ca.out_proj.bias, tf32=tf, round_dx=True)
+            y, y_r = self._add_ln(y, a, layer.norm2, self.layer_eps, p, tf, ca.out_proj.bias)
+            y, y_r = self._add_ln(y, self._ffn(layer, y_r, tf), layer.norm3, self.layer_eps, p, tf, layer.linear2.bias)
         return self._add_ln(y, None, self.decoder.norm, 1e-5, 0.0, tf)
 
     def _heads(self, h, h_r):

@@ -116,12 +116,13 @@ class EmbedOutput(Function):
 
 
 class AddLayerNorm(Function):
-    """y = LayerNorm_eps(x + dropout_p(a)); a may be None (final norms).
+    """y = LayerNorm_eps(x + dropout_p(a + a_bias)); a may be None (final norms); a_bias (may be None) is the
+    bias of the linear that produced a, folded in here so that its gradient falls out of the backward kernel.
     want_r: also return the TF32-rounded copy of y that feeds the next tensor-core GEMM;
     round_da: the gradient wrt a feeds tensor-core GEMMs only, so it is written rounded."""
 
     @staticmethod
-    def forward(ctx, x, a, gamma, beta, eps, p_drop, want_r=False, round_da=False):
+    def forward(ctx, x, a, a_bias, gamma, beta, eps, p_drop, want_r=False, round_da=False):
         _require_cuda(x, gamma)
         x = x.contiguous()
         a = a.contiguous() if a is not None else None
@@ -133,11 +134,11 @@ class AddLayerNorm(Function):
         s = torch.empty_like(x) if (need_grad and a is not None) else None
         stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
         seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
-        call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
+        call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), _ptr(a_bias), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
              seed, off, rows, d, y.data_ptr(), _ptr(y_r), _ptr(s), _ptr(stats), _stream())
         ctx.save_for_backward(s if s is not None else x, stats, gamma)
         ctx.has_a, ctx.p, ctx.seed, ctx.off = a is not None, (p_drop if a is not None else 0.0), seed, off
-        ctx.round_da = round_da
+        ctx.round_da, ctx.has_bias = round_da, a_bias is not None
         return (y, y_r) if want_r else y
 
     @staticmethod
@@ -149,16 +150,17 @@ class AddLayerNorm(Function):
         d = s.shape[-1]
         rows = s.numel() // d
         dx = torch.empty_like(s)
-        da = torch.empty_like(s) if (ctx.has_a and (ctx.p > 0 or ctx.round_da)) else None
+        da = torch.empty_like(s) if (ctx.has_a and (ctx.p > 0 or ctx.round_da or ctx.has_bias)) else None
         dgamma = torch.zeros_like(gamma)
         dbeta = torch.zeros_like(gamma)
+        dabias = torch.zeros_like(gamma) if ctx.has_bias else None
         ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=s.device, dtype=torch.uint8)
         call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed,
-             ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
-             _stream(), launches=2)
+             ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
+             ws.data_ptr(), _stream(), launches=2)
         if ctx.has_a and da is None:
             da = dx                      # no dropout, no rounding: same gradient flows to both summands
-        return dx, (da if ctx.has_a else None), dgamma, dbeta, None, None, None, None
+        return dx, (da if ctx.has_a else None), dabias, dgamma, dbeta, None, None, None, None
 
 
 class ReluDropout(Function):
@@ -204,21 +206,24 @@ def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, see
 
 
 def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, B, H, Lq, Lk, dh, kpm, causal, p_drop,
-              seed, off, impl, rnd=False, masks=(None, None)):
+              seed, off, impl, rnd=False, masks=(None, None), dbias=None):
     delta = torch.empty(B, H, Lq, device=o.device, dtype=torch.float32)
     if impl == 1 and p_drop > 0 and masks[0] is None:
         masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, o.device)
     a = AttnBwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), do.data_ptr(), H * dh, lse.data_ptr(), delta.data_ptr(),
                     dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl, int(rnd),
-                    _ptr(masks[0]), _ptr(masks[1]))
+                    _ptr(masks[0]), _ptr(masks[1]), _ptr(dbias) if impl == 1 else None)
     call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
 
 
 class SelfAttention(Function):
-    """K3/K4: attention core over the packed in-projection output qkv [B,L,3d]."""
+    """K3/K4: attention core over the packed in-projection output qkv [B,L,3d].
+    `bias` (may be None) is the in-projection bias PARAMETER: it is not used in the forward (the GEMM epilogue
+    already added it) but its gradient -- the column sums of dqkv -- is produced by the backward kernels, so
+    the projection's own backward skips it."""
 
     @staticmethod
-    def forward(ctx, qkv, kpm, H, causal, p_drop, impl, rnd=False):
+    def forward(ctx, qkv, bias, kpm, H, causal, p_drop, impl, rnd=False):
         _require_cuda(qkv)
         qkv = qkv.contiguous()
         B, L, d3 = qkv.shape
@@ -228,28 +233,32 @@ class SelfAttention(Function):
         o, lse, masks = _attn_fwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, B, H, L, L, d // H, kpm, causal, p_drop, seed, off,
                                   impl, any(ctx.needs_input_grad), qkv.device, rnd)
         ctx.save_for_backward(qkv, o, lse, kpm, *masks)
-        ctx.cfg = (H, causal, p_drop, seed, off, impl, rnd)
+        ctx.cfg = (H, causal, p_drop, seed, off, impl, rnd, bias is not None)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
         qkv, o, lse, kpm, m_rows, m_cols = ctx.saved_tensors
-        H, causal, p_drop, seed, off, impl, rnd = ctx.cfg
+        H, causal, p_drop, seed, off, impl, rnd, has_bias = ctx.cfg
         B, L, d3 = qkv.shape
         d = d3 // 3
         dqkv = torch.empty_like(qkv)
+        bimpl = impl if BWD_TC else 0
+        dbias = torch.zeros(d3, device=qkv.device, dtype=torch.float32) if (has_bias and bimpl == 1) else None
         base, g = qkv.data_ptr(), dqkv.data_ptr()
         _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
-                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, impl if BWD_TC else 0, rnd, (m_rows, m_cols))
-        return dqkv, None, None, None, None, None, None
+                  B, H, L, L, d // H, kpm, causal, p_drop, seed, off, bimpl, rnd, (m_rows, m_cols), dbias)
+        if has_bias and dbias is None:
+            dbias = dqkv.sum((0, 1))
+        return dqkv, dbias, None, None, None, None, None, None
 
 
 class CrossAttention(Function):
     """K5: queries q [B,Lq,d] against the packed memory projection kv [B,Lk,2d]."""
 
     @staticmethod
-    def forward(ctx, q, kv, kpm, H, p_drop, impl, rnd=False):
+    def forward(ctx, q, kv, bias, kpm, H, p_drop, impl, rnd=False):
         _require_cuda(q, kv)
         q, kv = q.contiguous(), kv.contiguous()
         B, Lq, d = q.shape
@@ -260,21 +269,25 @@ class CrossAttention(Function):
         o, lse, masks = _attn_fwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off,
                                   impl, need, q.device, rnd)
         ctx.save_for_backward(q, kv, o, lse, kpm, *masks)
-        ctx.cfg = (H, p_drop, seed, off, impl, rnd)
+        ctx.cfg = (H, p_drop, seed, off, impl, rnd, bias is not None)
         return o
 
     @staticmethod
     @once_differentiable
     def backward(ctx, do):
         q, kv, o, lse, kpm, m_rows, m_cols = ctx.saved_tensors
-        H, p_drop, seed, off, impl, rnd = ctx.cfg
+        H, p_drop, seed, off, impl, rnd, has_bias = ctx.cfg
         B, Lq, d = q.shape
         Lk = kv.shape[1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        bimpl = impl if BWD_TC else 0
+        dbias = torch.zeros(3 * d, device=q.device, dtype=torch.float32) if (has_bias and bimpl == 1) else None
         kb, gb = kv.data_ptr(), dkv.data_ptr()
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
-                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, impl if BWD_TC else 0, rnd, (m_rows, m_cols))
-        return dq, dkv, None, None, None, None, None
+                  d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, bimpl, rnd, (m_rows, m_cols), dbias)
+        if has_bias and dbias is None:
+            dbias = torch.cat([dq.sum((0, 1)), dkv.sum((0, 1))])
+        return dq, dkv, dbias, None, None, None, None, None
 
 
 def gemm_tf32(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, bias=None, relu=False, p_drop=0.0, seed=0, off=0,
@@ -342,10 +355,17 @@ class Linear(Function):
         dy2 = dy.reshape(M, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        want_db = has_b and ctx.needs_input_grad[2]
+        db = None
         if y is not None:
             dy2 = dy2.clone()
-            call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, 1, _stream())
-        db = dy2.sum(0) if (has_b and ctx.needs_input_grad[2]) else None
+            if want_db and N % 4 == 0 and N // 4 <= 256 and 256 % (N // 4) == 0:
+                db = torch.zeros(N, device=dy.device, dtype=torch.float32)     # bias grad = column sums, fused
+                call('pa_relu_dropout_bwd_colsum', y.data_ptr(), dy2.data_ptr(), M, N, p_drop, 1, db.data_ptr(), _stream())
+            else:
+                call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, 1, _stream())
+        if want_db and db is None:
+            db = dy2.sum(0)
         ldn = N
         if N % 4:                         # TMA needs a 16-byte row pitch (vocab head: N = 514)
             ldn = (N + 3) // 4 * 4
@@ -366,12 +386,14 @@ class Linear(Function):
 GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 
 
-def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False):
+def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True):
     """Dense projection y = x W[rows]^T + b[rows].
     tf32=True : our tcgen05 TF32 GEMM (training path; x must be a TF32-rounded tensor).
     tf32=False: cuBLAS fp32 through torch (exact path used by inference and PLANK_B200_GEMM=cublas)."""
     Wv = W if rows is None else W[rows]
     bv = b if (rows is None or b is None) else b[rows]
+    if tf32 and not bias_grad and bv is not None:
+        bv = bv.detach()                 # bias is added here, its gradient comes from the consumer kernel
     if tf32:
         W_r = tf32_weight(W)
         return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx)

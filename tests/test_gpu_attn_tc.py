@@ -41,10 +41,10 @@ def test_self_attention_tc_fwd(B, H, dh, L, causal, tail):
     q, k, v = qkv.double().cpu().split(d, -1)
     ref = attn_ref(q, k, v, kpm if tail else None, causal, H)
     ck = kpm.cuda().view(torch.uint8) if tail else None
-    out = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 1)
+    out = ops.SelfAttention.apply(qkv, None, ck, H, causal, 0.0, 1)
     torch.cuda.synchronize()
     err = rel_err(out.cpu(), ref)
-    exact = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 0)
+    exact = ops.SelfAttention.apply(qkv, None, ck, H, causal, 0.0, 0)
     print(f'B{B} H{H} dh{dh} L{L} causal={causal}: tc vs fp64 {err:.2e}; simt vs fp64 {rel_err(exact.cpu(), ref):.2e}')
     assert err < TOL
 
@@ -61,7 +61,7 @@ def test_cross_attention_tc_fwd(B, H, dh, Lq, Lk):
         kpm[b, max(1, Lk - 3 - 40 * b):] = True
     k, v = kv.double().cpu().split(d, -1)
     ref = attn_ref(q.double().cpu(), k, v, kpm, False, H)
-    out = ops.CrossAttention.apply(q, kv, kpm.cuda().view(torch.uint8), H, 0.0, 1)
+    out = ops.CrossAttention.apply(q, kv, None, kpm.cuda().view(torch.uint8), H, 0.0, 1)
     torch.cuda.synchronize()
     assert rel_err(out.cpu(), ref) < TOL
 
@@ -81,7 +81,7 @@ def test_tc_lse_and_backward_pairing():
     ops_bwd = ops.BWD_TC
     ops.BWD_TC = False                      # pair the tensor-core forward with the fp32 backward kernels
     try:
-        out = ops.SelfAttention.apply(qkv, None, H, True, 0.0, 1)
+        out = ops.SelfAttention.apply(qkv, None, None, H, True, 0.0, 1)
         (out * w.float().cuda()).sum().backward()
     finally:
         ops.BWD_TC = ops_bwd
@@ -99,9 +99,9 @@ def test_tc_dropout_matches_simt_mask():
     v = torch.eye(L)[None, :, None, :].expand(B, L, H, dh).reshape(B, L, d)
     qkv = tf32_round(torch.cat([q, k, v], -1))
     ops.RNG.seed, ops.RNG.counter = 1234, 100
-    o_tc = ops.SelfAttention.apply(qkv, None, H, False, p, 1)
+    o_tc = ops.SelfAttention.apply(qkv, None, None, H, False, p, 1)
     ops.RNG.seed, ops.RNG.counter = 1234, 100
-    o_simt = ops.SelfAttention.apply(qkv, None, H, False, p, 0)
+    o_simt = ops.SelfAttention.apply(qkv, None, None, H, False, p, 0)
     assert torch.equal(o_tc > 0, o_simt > 0)
     assert abs((o_tc > 0).float().mean().item() - (1 - p)) < 2e-2
     assert rel_err(o_tc.cpu(), o_simt.cpu()) < TOL
@@ -127,7 +127,7 @@ def test_self_attention_tc_bwd(B, H, dh, L, causal, tail):
     w = tf32_round(torch.randn(B, L, d, generator=g))
     (ref * w.double().cpu()).sum().backward()
     ck = kpm.cuda().view(torch.uint8) if tail else None
-    out = ops.SelfAttention.apply(qkv, ck, H, causal, 0.0, 1)
+    out = ops.SelfAttention.apply(qkv, None, ck, H, causal, 0.0, 1)
     (out * w).sum().backward()
     torch.cuda.synchronize()
     gq, gk, gv = qkv.grad.cpu().split(d, -1)
@@ -155,7 +155,7 @@ def test_cross_attention_tc_bwd(B, H, dh, Lq, Lk):
     ref = attn_ref(q64, k, v, kpm, False, H)
     w = tf32_round(torch.randn(B, Lq, d, generator=g))
     (ref * w.double().cpu()).sum().backward()
-    out = ops.CrossAttention.apply(q, kv, kpm.cuda().view(torch.uint8), H, 0.0, 1)
+    out = ops.CrossAttention.apply(q, kv, None, kpm.cuda().view(torch.uint8), H, 0.0, 1)
     (out * w).sum().backward()
     torch.cuda.synchronize()
     assert rel_err(q.grad.cpu(), q64.grad) < BWD_TOL
@@ -175,7 +175,7 @@ def test_tc_bwd_dropout_matches_fp32_kernels():
     for impl in (1, 0):
         qkv = base.clone().requires_grad_(True)
         ops.RNG.seed, ops.RNG.counter = 99, 7
-        out = ops.SelfAttention.apply(qkv, None, H, True, p, impl)
+        out = ops.SelfAttention.apply(qkv, None, None, H, True, p, impl)
         (out * w).sum().backward()
         grads.append(qkv.grad.clone())
     torch.cuda.synchronize()

@@ -152,3 +152,18 @@ def test_rounded_operands_remove_truncation_bias():
     e_raw, e_rn = rel_err(c_raw.cpu(), ref), rel_err(c_rn.cpu(), ref)
     print(f'raw (truncated) operands: {e_raw:.2e}; round-to-nearest operands: {e_rn:.2e}')
     assert e_rn < 0.5 * e_raw and e_rn < 4e-4
+
+
+def test_linear_relu_dropout_bias_gradient_fused():
+    """relu+dropout epilogue: backward's fused column-sum kernel must equal the masked gradient's column sums."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    M, K, N = 1000, 512, 1024
+    x = torch.randn(M, K, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=g).cuda().requires_grad_(True)
+    out = ops.Linear.apply(x, w, b, w.detach(), True, 0.2, False, False)
+    gy = torch.randn(M, N, generator=g).cuda()
+    (out * gy).sum().backward()
+    masked = gy * (out.detach() > 0) / 0.8
+    assert rel_err(b.grad.cpu(), masked.sum(0).cpu()) < 2e-3

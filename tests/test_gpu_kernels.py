@@ -75,7 +75,7 @@ def test_add_ln_fwd_bwd(ops, d, eps, with_a):
     (ref * w).sum().backward()
     cx, cg, cb = (t.detach().to(dev()).requires_grad_(True) for t in (x, gamma, beta))
     ca = a.detach().to(dev()).requires_grad_(True) if with_a else None
-    out = ops.AddLayerNorm.apply(cx, ca, cg, cb, eps, 0.0)
+    out = ops.AddLayerNorm.apply(cx, ca, None, cg, cb, eps, 0.0)
     assert rel_err(out.cpu(), ref.detach()) < 2e-6
     (out * w.to(dev())).sum().backward()
     assert rel_err(cx.grad.cpu(), x.grad) < 1e-5
@@ -94,7 +94,7 @@ def test_add_ln_dropout_mask_consistent(ops):
     gamma = torch.ones(d, device=dev(), requires_grad=True)
     beta = torch.zeros(d, device=dev(), requires_grad=True)
     # eps huge => y ~ (s-mean)/sqrt(eps): recover s = dropout(a) up to the row mean via the saved tensor instead
-    y = ops.AddLayerNorm.apply(x, a, gamma, beta, 1.0, p)
+    y = ops.AddLayerNorm.apply(x, a, None, gamma, beta, 1.0, p)
     s = y.grad_fn.saved_tensors[0]
     keep = (s > 0)
     assert abs(keep.float().mean().item() - (1 - p)) < 5e-3
@@ -156,7 +156,7 @@ def test_self_attention_fwd_bwd(ops, B, H, dh, L, causal, tail):
     (ref * w).sum().backward()
     cq = qkv.detach().float().to(dev()).requires_grad_(True)
     ck = kpm.to(dev()).view(torch.uint8) if tail else None
-    out = ops.SelfAttention.apply(cq, ck, H, causal, 0.0, 0)
+    out = ops.SelfAttention.apply(cq, None, ck, H, causal, 0.0, 0)
     assert rel_err(out.cpu(), ref.detach()) < 5e-6
     (out * w.float().to(dev())).sum().backward()
     assert rel_err(cq.grad.cpu(), qkv.grad) < 2e-5
@@ -177,7 +177,7 @@ def test_cross_attention_fwd_bwd(ops, B, H, dh, Lq, Lk):
     (ref * w).sum().backward()
     cq = q.detach().float().to(dev()).requires_grad_(True)
     ckv = kv.detach().float().to(dev()).requires_grad_(True)
-    out = ops.CrossAttention.apply(cq, ckv, kpm.to(dev()).view(torch.uint8), H, 0.0, 0)
+    out = ops.CrossAttention.apply(cq, ckv, None, kpm.to(dev()).view(torch.uint8), H, 0.0, 0)
     assert rel_err(out.cpu(), ref.detach()) < 5e-6
     (out * w.float().to(dev())).sum().backward()
     assert rel_err(cq.grad.cpu(), q.grad) < 2e-5
@@ -195,7 +195,7 @@ def test_attention_dropout_fwd_bwd_consistent(ops):
     v = torch.eye(L)[None, :, None, :].expand(B, L, H, dh).reshape(B, L, d).contiguous()
     qkv = torch.cat([q, k, v], -1)
     cq = qkv.to(dev()).requires_grad_(True)
-    out = ops.SelfAttention.apply(cq, None, H, False, p, 0)
+    out = ops.SelfAttention.apply(cq, None, None, H, False, p, 0)
     pd = out.detach().cpu().view(B, L, H, dh).transpose(1, 2)            # [B,H,L,L] dropped probs
     q64 = qkv.double().requires_grad_(True)
     qq, kk, vv = q64.split(d, -1)
@@ -287,3 +287,44 @@ def test_decode_attn_matches_oracle():
          None, ckpm.data_ptr(), B, H, dh, dh ** -0.5, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
     ref = attn_ref(q[:, None].double(), kv[..., :d].double(), kv[..., d:].double(), kpm, False, H)[:, 0]
     assert rel_err(o.cpu(), ref) < 5e-6
+
+
+def test_add_ln_folded_linear_bias(ops):
+    """y = LN(x + a + bias): the bias of the producing linear folded into the LN kernels; its gradient
+    (column sums of da) must come out of the backward kernel."""
+    g = torch.Generator().manual_seed(31)
+    rows, d = 515, 512
+    x = torch.randn(rows, d, generator=g, requires_grad=True)
+    a = torch.randn(rows, d, generator=g, requires_grad=True)
+    bias = torch.randn(d, generator=g, requires_grad=True)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, generator=g)).requires_grad_(True)
+    ref = F.layer_norm(x + a + bias, (d,), gamma, beta, 1.0)
+    w = torch.randn(rows, d, generator=g)
+    (ref * w).sum().backward()
+    c = [t.detach().to(dev()).requires_grad_(True) for t in (x, a, bias, gamma, beta)]
+    out = ops.AddLayerNorm.apply(c[0], c[1], c[2], c[3], c[4], 1.0, 0.0)
+    assert rel_err(out.cpu(), ref.detach()) < 2e-6
+    (out * w.to(dev())).sum().backward()
+    for ours, theirs in zip(c, (x, a, bias, gamma, beta)):
+        assert rel_err(ours.grad.cpu(), theirs.grad) < 1e-5
+
+
+def test_attention_bwd_bias_gradient(ops):
+    """The tensor-core backward kernels also emit the in-projection bias gradient (column sums of dqkv)."""
+    g = torch.Generator().manual_seed(32)
+    B, H, dh, L = 2, 8, 64, 200
+    d = H * dh
+    qkv = torch.randn(B, L, 3 * d, generator=g).to(dev()).requires_grad_(True)
+    bias = torch.zeros(3 * d, device=dev(), requires_grad=True)
+    w = torch.randn(B, L, d, generator=g).to(dev())
+    out = ops.SelfAttention.apply(qkv, bias, None, H, True, 0.0, 1)
+    (out * w).sum().backward()
+    assert rel_err(bias.grad.cpu(), qkv.grad.sum((0, 1)).cpu()) < 1e-5
+    q = torch.randn(B, 70, d, generator=g).to(dev()).requires_grad_(True)
+    kv = torch.randn(B, L, 2 * d, generator=g).to(dev()).requires_grad_(True)
+    bias2 = torch.zeros(3 * d, device=dev(), requires_grad=True)
+    out = ops.CrossAttention.apply(q, kv, bias2, None, H, 0.0, 1)
+    (out * torch.randn(B, 70, d, generator=g).to(dev())).sum().backward()
+    ref = torch.cat([q.grad.sum((0, 1)), kv.grad.sum((0, 1))])
+    assert rel_err(bias2.grad.cpu(), ref.cpu()) < 1e-5
