@@ -167,6 +167,11 @@ int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const in
 int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
                        float* dists, void* stream);
 
+/* Exact-fp32 small-M projection for the decode step: C[M,N] = X[M,K] W[N,K]^T + bias (relu optional).
+ * K % 32 == 0 and K <= 1536 (the W slice of a CTA lives in smem). */
+int pa_gemm_skinny_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* c,
+                       int64_t ldc, int M, int N, int K, int relu, void* stream);
+
 /* ---- K11/K12: KV-cached greedy decode step pieces (replace the O(T^3) loop models.py:284-307).
  * All state lives in caller-owned device buffers; `t` is the 0-based step.  When `t_dev` is not NULL the
  * step index is read from device memory instead, so that ONE captured CUDA graph replays every step;

@@ -110,7 +110,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tc::tma_load_2d(sa, &tma_a, kb * BK, b * p.a_batch_rows + mt * BM, full_bar + stage);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tc::tma_load_2d(sa + j * (BK * 128), &tma_a, mt * BM + j * 32, kb * BK, full_bar + stage);
+            for (int j = 0; j < BM / 32; ++j) tc::tma_load_2d(sa + j * (BK * 128), &tma_a, mt * BM + j * 32, b * p.a_batch_rows + kb * BK, full_bar + stage);
           }
           if constexpr (!B_MN) {
             tc::tma_load_2d(sb, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN, full_bar + stage);
@@ -287,7 +287,7 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   CUtensorMap ta, tb, tc_map;
   int rc;
   if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
-  else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 4, 32, BK, true);
+  else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.K), (uint64_t)a.lda * 4, 32, BK, true);
   if (rc) return rc;
   if (!B_MN) rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.N), (uint64_t)a.ldb * 4, BK, BN);
   else rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.N, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.K), (uint64_t)a.ldb * 4, 32, BK, true);
@@ -343,7 +343,9 @@ int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
 extern "C" int pa_gemm_tf32(const pa_gemm_args* a, void* stream) {
   PA_CHECK_ARG(a != nullptr && a->M > 0 && a->N > 0 && a->K > 0);
   PA_CHECK_ARG(a->lda % 4 == 0 && a->ldb % 4 == 0);
-  PA_CHECK_ARG(!(a->batch > 1 && (a->a_mn || a->split_k > 1)));
+  PA_CHECK_ARG(!(a->batch > 1 && a->split_k > 1));
+  // batched MN-major operands: the contraction must not run past a batch's rows (no zero fill between batches)
+  PA_CHECK_ARG(!(a->batch > 1 && (a->a_mn || a->b_mn) && a->K % 32 != 0));
   PA_CHECK_ARG(!(a->split_k > 1 && !a->accumulate));
   PA_CHECK_ARG(!(a->accumulate && (a->bias != nullptr || a->relu || a->p_drop > 0.f)));
   cudaStream_t st = (cudaStream_t)stream;

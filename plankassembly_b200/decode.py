@@ -39,6 +39,7 @@ class GreedyDecoder:
         self.use_graph = os.environ.get('PLANK_B200_DECODE_GRAPH', '1') == '1'
         self._key = None
         self.graph = None
+        self._lin_out = {}
 
     # ------------------------------------------------------------------ persistent state
     def _buffers(self, B, S, device):
@@ -62,6 +63,17 @@ class GreedyDecoder:
         self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)
         self._key, self.graph = key, None
 
+    def _lin(self, x, W, b, key, relu=False):
+        """y = x W^T + b in exact fp32 through pa_gemm_skinny_f32; outputs live in persistent buffers."""
+        M, K = x.shape
+        N = W.shape[0]
+        out = self._lin_out.get(key)
+        if out is None or out.shape != (M, N) or out.device != x.device:
+            out = self._lin_out[key] = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        call('pa_gemm_skinny_f32', x.data_ptr(), x.stride(0), W.data_ptr(), W.stride(0), b.data_ptr() if b is not None else None,
+             out.data_ptr(), N, M, N, K, int(relu), _stream())
+        return out
+
     def _add_ln(self, x, a, norm, eps, out):
         call('pa_add_ln_fwd', x.data_ptr(), a.data_ptr() if a is not None else None, None, norm.weight.data_ptr(),
              norm.bias.data_ptr(), eps, 0.0, 0, 0, x.shape[0], x.shape[1], out.data_ptr(), None, None, None, _stream())
@@ -81,25 +93,25 @@ class GreedyDecoder:
              m.query_coord_embedding.weight.data_ptr(), m.query_pos_embedding.weight.data_ptr(), d, y.data_ptr(), _stream())
         for li, l in enumerate(m.decoder.layers):
             sa, ca = l.self_attn, l.multihead_attn
-            qkv = F.linear(y, sa.in_proj_weight, sa.in_proj_bias)                              # [B,3d]
+            qkv = self._lin(y, sa.in_proj_weight, sa.in_proj_bias, ('qkv', li))                 # [B,3d]
             base = qkv.data_ptr()
             call('pa_decode_attn', base, 3 * d, base + 4 * d, base + 8 * d, 3 * d, self.self_k[li].data_ptr(),
                  self.self_v[li].data_ptr(), T, d, t, t + 1, t_dev, None, B, H, dh, scale, self.o.data_ptr(), _stream())
-            a = F.linear(self.o, sa.out_proj.weight, sa.out_proj.bias)
+            a = self._lin(self.o, sa.out_proj.weight, sa.out_proj.bias, ('so', li))
             y, other = self._add_ln(y, a, l.norm1, m.layer_eps, other), y
-            q = F.linear(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
+            q = self._lin(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d], ('cq', li))
             kvb = self.cross_kv[li].data_ptr()
             call('pa_decode_attn', q.data_ptr(), d, None, None, 0, kvb, kvb + 4 * d, S, 2 * d, 0, S, None, self.kpm.data_ptr(),
                  B, H, dh, scale, self.o.data_ptr(), _stream())
-            a = F.linear(self.o, ca.out_proj.weight, ca.out_proj.bias)
+            a = self._lin(self.o, ca.out_proj.weight, ca.out_proj.bias, ('co', li))
             y, other = self._add_ln(y, a, l.norm2, m.layer_eps, other), y
-            h = torch.relu_(F.linear(y, l.linear1.weight, l.linear1.bias))
-            f = F.linear(h, l.linear2.weight, l.linear2.bias)
+            h = self._lin(y, l.linear1.weight, l.linear1.bias, ('f1', li), relu=True)
+            f = self._lin(h, l.linear2.weight, l.linear2.bias, ('f2', li))
             y, other = self._add_ln(y, f, l.norm3, m.layer_eps, other), y
         hfin_t = self._add_ln(y, None, m.decoder.norm, 1e-5, other)
-        lv = F.linear(hfin_t, m.vocab_head.weight, m.vocab_head.bias)
-        pf = F.linear(hfin_t, m.pointer_head.weight, m.pointer_head.bias)
-        sw = F.linear(hfin_t, m.switch_head.weight, m.switch_head.bias)
+        lv = self._lin(hfin_t, m.vocab_head.weight, m.vocab_head.bias, 'lv')
+        pf = self._lin(hfin_t, m.pointer_head.weight, m.pointer_head.bias, 'pf')
+        sw = self._lin(hfin_t, m.switch_head.weight, m.switch_head.bias, 'sw')
         call('pa_decode_head', hfin_t.data_ptr(), lv.data_ptr(), pf.data_ptr(), sw.data_ptr(), self.hfin.data_ptr(), T, B, d,
              V, t, t_dev, m.token.END, self.samples.data_ptr(), self.attach.data_ptr(), T, self.first_end.data_ptr(), _stream())
         if t_dev is not None:

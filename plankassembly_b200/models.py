@@ -194,8 +194,8 @@ class PlankModel(nn.Module):
     def _heads(self, h, h_r):
         tf = self._tf32()
         lv = ops.linear(h_r, self.vocab_head.weight, self.vocab_head.bias, tf32=tf)
-        pf = ops.linear(h_r, self.pointer_head.weight, self.pointer_head.bias, tf32=tf)
-        lp = torch.bmm(pf, h.transpose(1, 2))                      # raw scores; 1/d applied in the kernel
+        pf = ops.linear(h_r, self.pointer_head.weight, self.pointer_head.bias, tf32=tf, round_out=True)
+        lp = ops.pointer_scores(pf, h_r, tf)                       # raw scores; 1/d applied in the kernel
         sw = F.linear(h, self.switch_head.weight, self.switch_head.bias).squeeze(-1)
         return lv, lp, sw
 

@@ -383,6 +383,43 @@ class Linear(Function):
         return dx, dW, db, None, None, None, None, None
 
 
+class PointerScores(Function):
+    """Raw pointer scores lp[b] = pf[b] h[b]^T (ref models.py:149; the 1/d and the masking live in the
+    distribution kernel) as one batched tcgen05 TF32 GEMM; backward = two batched GEMMs with MN-major operands:
+    dpf[b] = dlp[b] h[b],  dh[b] = dlp[b]^T pf[b]."""
+
+    @staticmethod
+    def forward(ctx, pf, h):
+        _require_cuda(pf, h)
+        pf, h = pf.contiguous(), h.contiguous()
+        B, T, d = pf.shape
+        lp = torch.empty(B, T, T, device=pf.device, dtype=torch.float32)
+        gemm_tf32(pf, h, lp, T, T, d, lda=d, ldb=d, ldc=T, batch=B, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T)
+        ctx.save_for_backward(pf, h)
+        return lp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlp):
+        pf, h = ctx.saved_tensors
+        B, T, d = pf.shape
+        dlp = dlp.contiguous()
+        dpf, dh = torch.empty_like(pf), torch.empty_like(h)
+        gemm_tf32(dlp, h, dpf, T, d, T, lda=T, ldb=d, ldc=d, b_mn=True, batch=B, a_batch_rows=T, b_batch_rows=T,
+                  c_batch_stride=T * d, round_out=True)
+        gemm_tf32(dlp, pf, dh, T, d, T, lda=T, ldb=d, ldc=d, a_mn=True, b_mn=True, batch=B, a_batch_rows=T, b_batch_rows=T,
+                  c_batch_stride=T * d)
+        return dpf, dh
+
+
+def pointer_scores(pf, h, tf32):
+    """lp = pf @ h^T per sequence: tensor-core batched GEMM on the TF32 path (needs T % 32 == 0 for the
+    MN-major backward operands), fp32 cuBLAS bmm on the exact path."""
+    if tf32 and pf.shape[1] % 32 == 0:
+        return PointerScores.apply(pf, h)
+    return torch.bmm(pf, h.transpose(1, 2))
+
+
 GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 
 

@@ -167,3 +167,21 @@ def test_linear_relu_dropout_bias_gradient_fused():
     (out * gy).sum().backward()
     masked = gy * (out.detach() > 0) / 0.8
     assert rel_err(b.grad.cpu(), masked.sum(0).cpu()) < 2e-3
+
+
+def test_pointer_scores_autograd():
+    """Batched pointer scoring (ref models.py:149) forward + both backward GEMMs against fp64 bmm."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for B, T, d in [(3, 256, 512), (4, 64, 128), (2, 128, 256)]:
+        pf = torch.randn(B, T, d, generator=g, dtype=torch.float64, requires_grad=True)
+        h = torch.randn(B, T, d, generator=g, dtype=torch.float64, requires_grad=True)
+        ref = torch.bmm(pf, h.transpose(1, 2))
+        w = torch.randn(B, T, T, generator=g, dtype=torch.float64)
+        (ref * w).sum().backward()
+        cpf, ch = (t.detach().float().cuda().requires_grad_(True) for t in (pf, h))
+        out = ops.pointer_scores(cpf, ch, True)
+        assert rel_err(out.cpu(), ref.detach()) < 2e-3
+        (out * w.float().cuda()).sum().backward()
+        assert rel_err(cpf.grad.cpu(), pf.grad) < 2e-3, (B, T, d)
+        assert rel_err(ch.grad.cpu(), h.grad) < 2e-3, (B, T, d)

@@ -328,3 +328,19 @@ def test_attention_bwd_bias_gradient(ops):
     (out * torch.randn(B, 70, d, generator=g).to(dev())).sum().backward()
     ref = torch.cat([q.grad.sum((0, 1)), kv.grad.sum((0, 1))])
     assert rel_err(bias2.grad.cpu(), ref.cpu()) < 1e-5
+
+
+def test_gemm_skinny_f32_exact():
+    """Decode projections: fp32 FMA GEMM against fp64; must be at fp32 rounding level (not TF32)."""
+    from plankassembly_b200._lib import call
+    g = torch.Generator().manual_seed(33)
+    for M, N, K, relu in [(64, 1536, 512, False), (64, 512, 1024, False), (64, 1024, 512, True), (4, 514, 128, False), (7, 1, 256, False), (130, 384, 128, False)]:
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+        cx, cw, cb = x.to(dev()), w.to(dev()), b.to(dev())
+        out = torch.full((M, N), float('nan'), device=dev())
+        call('pa_gemm_skinny_f32', cx.data_ptr(), K, cw.data_ptr(), K, cb.data_ptr(), out.data_ptr(), N, M, N, K, int(relu),
+             torch.cuda.current_stream().cuda_stream)
+        ref = x.double() @ w.double().T + b.double()
+        if relu:
+            ref = torch.relu(ref)
+        assert rel_err(out.cpu(), ref) < 2e-6, (M, N, K)
