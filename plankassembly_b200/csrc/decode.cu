@@ -36,25 +36,35 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
 #pragma unroll
   for (int c = 0; c < F; ++c) qr[c] = q[(int64_t)b * ldq + h * DH + sub * F + c];
   float mx = -INFINITY;
-  for (int j0 = warp * 4; j0 < len; j0 += (kThreads / 32) * 4) {
-    const int j = j0 + grp;
-    float acc = 0.f;
-    if (j < len) {
-      const float* kr = kc + (int64_t)j * ldc + sub * F;
+  // 4 keys per warp pass, 4 passes unrolled: 8 independent 16-byte loads in flight per lane
+  for (int j0 = warp * 4; j0 < len; j0 += (kThreads / 32) * 4 * 4) {
+    float acc[4];
 #pragma unroll
-      for (int c = 0; c < F; c += 4) {
-        float4 kk = *reinterpret_cast<const float4*>(kr + c);
-        acc += qr[c] * kk.x + qr[c + 1] * kk.y + qr[c + 2] * kk.z + qr[c + 3] * kk.w;
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * (kThreads / 32) * 4 + grp;
+      acc[u] = 0.f;
+      if (j < len) {
+        const float* kr = kc + (int64_t)j * ldc + sub * F;
+#pragma unroll
+        for (int c = 0; c < F; c += 4) {
+          float4 kk = *reinterpret_cast<const float4*>(kr + c);
+          acc[u] += qr[c] * kk.x + qr[c + 1] * kk.y + qr[c + 2] * kk.z + qr[c + 3] * kk.w;
+        }
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (j < len && sub == 0) {
-      float s = acc * scale;
-      if (kpm != nullptr && kpm[(int64_t)b * len + j]) s = -INFINITY;
-      s_p[j] = s;
-      mx = fmaxf(mx, s);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * (kThreads / 32) * 4 + grp;
+      float a = acc[u];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      if (j < len && sub == 0) {
+        float s = a * scale;
+        if (kpm != nullptr && kpm[(int64_t)b * len + j]) s = -INFINITY;
+        s_p[j] = s;
+        mx = fmaxf(mx, s);
+      }
     }
   }
   mx = warp_max(mx);
@@ -78,11 +88,20 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
   float acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
-  for (int j = warp; j < len; j += kThreads / 32) {
-    const float p = s_p[j];
-    const float* vr = vc + (int64_t)j * ldc + lane * C;
+  for (int j0 = warp; j0 < len; j0 += (kThreads / 32) * 8) {      // 8 key rows in flight per warp
+    float vv[8][C], pp[8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] += p * vr[c];
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * (kThreads / 32);
+      pp[u] = j < len ? s_p[j] : 0.f;
+      const float* vr = vc + (int64_t)min(j, len - 1) * ldc + lane * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) vv[u][c] = vr[c];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] += pp[u] * vv[u][c];
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) s_o[warp][lane * C + c] = acc[c];
