@@ -17,6 +17,7 @@
 #include "tc_common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -48,7 +49,9 @@ template <int BN> struct Cfg {
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// CL = 2: CTA pairs (cluster of 2 along M) share every B (weight) tile: each CTA fetches half of it and TMA
+// multicasts the half into both CTAs' smem -> 1/3 less L2->smem traffic per CTA (the K=512 GEMMs are L2-bound).
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
@@ -68,17 +71,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
     if (p.tma_store) tc::tma_prefetch_desc(&tma_c);
-    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, CL); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) tc::cluster_sync();      // the peer's barriers exist before anything is multicast into it
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = CL > 1 ? (int)tc::cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
+  const int m_groups = (p.m_tiles + CL - 1) / CL;   // an m group = the CL consecutive m tiles of one cluster step
 
-  const int tiles_per_batch = p.m_tiles * p.n_tiles * p.split_k;
+  const int tiles_per_batch = m_groups * p.n_tiles * p.split_k;
   const int num_tiles = tiles_per_batch * p.batch;
   const int k_blocks_total = (p.K + BK - 1) / BK;
   const int k_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
@@ -86,10 +93,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   auto decode = [&](int tile, int& b, int& mt, int& nt, int& kb0, int& kb1) {
     b = tile / tiles_per_batch;
     int r = tile - b * tiles_per_batch;
-    int sp = r / (p.m_tiles * p.n_tiles);
-    r -= sp * p.m_tiles * p.n_tiles;
-    mt = r / p.n_tiles;            // n fastest: an activation tile is reused by all its n tiles out of L2
-    nt = r - mt * p.n_tiles;
+    int sp = r / (m_groups * p.n_tiles);
+    r -= sp * m_groups * p.n_tiles;
+    mt = (r / p.n_tiles) * CL + crank;   // n fastest: an activation tile is reused by all its n tiles out of L2
+    nt = r % p.n_tiles;
     kb0 = sp * k_per_split;
     kb1 = min(k_blocks_total, kb0 + k_per_split);
   };
@@ -98,7 +105,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int b, mt, nt, kb0, kb1;
         decode(tile, b, mt, nt, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -112,11 +119,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j) tc::tma_load_2d(sa + j * (BK * 128), &tma_a, mt * BM + j * 32, b * p.a_batch_rows + kb * BK, full_bar + stage);
           }
-          if constexpr (!B_MN) {
-            tc::tma_load_2d(sb, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN, full_bar + stage);
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!B_MN) {
+              tc::tma_load_2d(sb, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN, full_bar + stage);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(sb + j * (BK * 128), &tma_b, nt * BN + j * 32, b * p.b_batch_rows + kb * BK, full_bar + stage);
+              for (int j = 0; j < BN / 32; ++j) tc::tma_load_2d(sb + j * (BK * 128), &tma_b, nt * BN + j * 32, b * p.b_batch_rows + kb * BK, full_bar + stage);
+            }
+          } else {   // this CTA fetches its half of the B tile and multicasts it into both CTAs of the pair
+            if constexpr (!B_MN) {
+              tc::tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN + crank * (BN / 2), full_bar + stage, 0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) {
+                const int jj = crank * (BN / 64) + j;
+                tc::tma_load_2d_mcast(sb + jj * (BK * 128), &tma_b, nt * BN + jj * 32, b * p.b_batch_rows + kb * BK, full_bar + stage, 0x3);
+              }
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -128,7 +147,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int b, mt, nt, kb0, kb1;
         decode(tile, b, mt, nt, kb0, kb1);
         tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -149,7 +168,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t dbk = tc::desc_advance(db, B_MN ? k * 1024 : k * UK * 4);
             tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc::tc_commit(empty_bar + stage);            // frees the smem slot when these MMAs retire
+          if constexpr (CL > 1) tc::tc_commit_mcast(empty_bar + stage, 0x3);   // the slot is shared: both CTAs must be done with it
+          else tc::tc_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         tc::tc_commit(tmem_full + acc);                // accumulator complete -> epilogue
@@ -162,7 +182,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       int b, mt, nt, kb0, kb1;
       decode(tile, b, mt, nt, kb0, kb1);
       // stage this tile's bias slice in smem once (per-element global loads serialised the epilogue)
@@ -264,6 +284,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (p.tma_store && warp >= 2 && lane == 0) tc::tma_store_wait_all();
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) tc::cluster_sync();      // do not exit while the peer may still multicast / arrive here
   if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
@@ -281,15 +302,15 @@ void resolve_encode() {
     g_encode = (EncodeFn)fn;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const pa_gemm_args& a, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, int CL>
+int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb, tc_map;
   int rc;
   if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
   else rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.M, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.K), (uint64_t)a.lda * 4, 32, BK, true);
   if (rc) return rc;
-  if (!B_MN) rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.N), (uint64_t)a.ldb * 4, BK, BN);
+  if (!B_MN) rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.N), (uint64_t)a.ldb * 4, BK, BN / CL);
   else rc = pa_make_tmap_2d(&tb, a.b, (uint64_t)a.N, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.b_batch_rows : a.K), (uint64_t)a.ldb * 4, 32, BK, true);
   if (rc) return rc;
   GemmParams p{};
@@ -308,17 +329,36 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
   } else {
     tc_map = ta;
   }
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_done = true;
   }
-  int tiles = p.m_tiles * p.n_tiles * p.split_k * p.batch;
-  int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, tc_map, p);
+  int tiles = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.split_k * p.batch;      // cluster steps
+  int grid = (tiles * CL < kNumSMs ? tiles * CL : (kNumSMs / CL) * CL);
+  if constexpr (CL == 1) {
+    kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, tc_map, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    PA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc_map, p));
+  }
   PA_CHECK_LAUNCH();
   return PA_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const pa_gemm_args& a, cudaStream_t st) {
+  // CTA pairs pay off once there are enough m tiles to pair up; tiny problems keep the single-CTA kernel
+  static const bool pair_ok = getenv("PLANK_B200_GEMM_PAIR") == nullptr || getenv("PLANK_B200_GEMM_PAIR")[0] != '0';
+  const int m_tiles = (a.M + BM - 1) / BM;
+  if (pair_ok && m_tiles >= 2 && m_tiles % 2 == 0) return launch_cl<BN, A_MN, B_MN, 2>(a, st);
+  return launch_cl<BN, A_MN, B_MN, 1>(a, st);
 }
 
 }  // namespace
