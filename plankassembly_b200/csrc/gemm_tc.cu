@@ -4,7 +4,9 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
 //   warp 1      MMA issuer    (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM owner
-//   warps 2..5  epilogue      (tcgen05.ld 32x32b -> bias/ReLU/Philox dropout -> 16-byte stores)
+//   warps 2..9  epilogue      (tcgen05.ld 32x32b -> bias/ReLU/Philox dropout/TF32 rounding -> 128B-swizzled smem
+//                              tile -> TMA store or reduce-add); two warps per TMEM lane quarter take alternate
+//                              32-column chunks, each with its own staging tile
 // Three pipelines: smem full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators
 // (MMA <-> epilogue), static persistent tile schedule.
 //
@@ -24,7 +26,7 @@ namespace {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 32;         // 32 tf32 = 128 B = one swizzle row
 constexpr int UK = 8;          // K per tcgen05.mma.kind::tf32
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct GemmParams {
   float* c; int64_t ldc; int64_t c_batch_stride;
@@ -35,6 +37,7 @@ struct GemmParams {
   int relu; float p_drop; uint64_t seed, offset;
   float alpha;
   int round_out;
+  int debug;              // bit 0: skip the epilogue body (mainloop-only timing experiments)
   int tma_store;          // epilogue stores through smem + TMA (needs a 16-byte row pitch)
   int m_tiles, n_tiles;
 };
@@ -44,8 +47,8 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 4;           // 16 KB
   static constexpr int kBBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageOut = 4 * 32 * 128;        // per epilogue warp: one 32x32 fp32 tile, 128B-swizzled
-  static constexpr int kSmem = kStages * kStageBytes + kStageOut + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
+  static constexpr int kStageOut = 8 * 32 * 128;        // per epilogue warp: one 32x32 fp32 tile, 128B-swizzled
+  static constexpr int kSmem = kStages * kStageBytes + kStageOut + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
 };
 
@@ -58,13 +61,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [4 warps][32 rows][128 B]
+  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [8 warps][32 rows][128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + C::kStageOut);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(out_stage + C::kStageOut + 256);   // [2][BN]
+  float* bias_s = reinterpret_cast<float*>(out_stage + C::kStageOut + 256);   // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -72,7 +75,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tc::tma_prefetch_desc(&tma_b);
     if (p.tma_store) tc::tma_prefetch_desc(&tma_c);
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, CL); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 8); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -179,6 +182,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ===================================== epilogue =========================================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                  // which of the quarter's two warps: takes chunks half, half+2, ...
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
@@ -187,18 +191,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       decode(tile, b, mt, nt, kb0, kb1);
       // stage this tile's bias slice in smem once (per-element global loads serialised the epilogue)
       if (p.bias != nullptr) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // everyone is done with the previous tile's bias
         const int et = threadIdx.x - 64;
-        for (int c = et; c < BN; c += 128) bias_s[acc * BN + c] = (nt * BN + c < p.N) ? __ldg(p.bias + nt * BN + c) : 0.f;
+        if (et < BN) bias_s[et] = (nt * BN + et < p.N) ? __ldg(p.bias + nt * BN + et) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       tc::mbar_wait(tmem_full + acc, acc_phase);
       tc::tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       float* crow = p.c + (int64_t)b * p.c_batch_stride + (int64_t)row * p.ldc;
-      uint8_t* my_stage = out_stage + q * (32 * 128);
+      uint8_t* my_stage = out_stage + (warp - 2) * (32 * 128);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < ((p.debug & 1) ? 0 : BN); c0 += 64) {
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
         tc::tmem_ld_wait();
@@ -214,7 +219,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float x = __uint_as_float(r[j + e]) * p.alpha;
-                if (p.bias != nullptr) x += bias_s[acc * BN + c0 + j + e];
+                if (p.bias != nullptr) x += bias_s[c0 + j + e];
                 if (p.relu) x = fmaxf(x, 0.f);
                 v[e] = x;
               }
@@ -248,7 +253,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float x = __uint_as_float(r[j + e]) * p.alpha;
-              if (p.bias != nullptr) x += bias_s[acc * BN + c0 + j + e];
+              if (p.bias != nullptr) x += bias_s[c0 + j + e];
               if (p.relu) x = fmaxf(x, 0.f);
               v[e] = x;
             }
@@ -320,6 +325,7 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   p.split_k = a.split_k < 1 ? 1 : a.split_k; p.accumulate = a.accumulate;
   p.relu = a.relu; p.p_drop = a.p_drop; p.seed = a.seed; p.offset = a.offset; p.alpha = a.alpha; p.round_out = a.round_out;
   p.m_tiles = (a.M + BM - 1) / BM; p.n_tiles = (a.N + BN - 1) / BN;
+  { const char* dbg = getenv("PLANK_B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
   p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
                 (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));

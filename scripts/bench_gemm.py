@@ -1,0 +1,26 @@
+"""Isolated timing of the tensor-core GEMM on the model's shapes (GPU only)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from plankassembly_b200 import ops
+shapes = [('qkv  fwd', 32768, 1536, 512, {}), ('out  fwd', 32768, 512, 512, {}), ('ffn1 fwd', 32768, 1024, 512, {}), ('ffn2 fwd', 32768, 512, 1024, {}),
+          ('qkv  dX ', 32768, 512, 1536, {'b_mn': True}), ('qkv  dW ', 1536, 512, 32768, {'a_mn': True, 'b_mn': True, 'split_k': 6, 'accumulate': True})]
+for name, M, N, K, kw in shapes:
+    if kw.get('a_mn'):
+        a = torch.randn(K, M, device='cuda'); lda = M
+    else:
+        a = torch.randn(M, K, device='cuda'); lda = K
+    if kw.get('b_mn'):
+        b = torch.randn(K, N, device='cuda'); ldb = N
+    else:
+        b = torch.randn(N, K, device='cuda'); ldb = K
+    c = torch.zeros(M, N, device='cuda')
+    bias = None if kw else torch.randn(N, device='cuda')
+    f = lambda: ops.gemm_tf32(a, b, c, M, N, K, lda=lda, ldb=ldb, ldc=N, bias=bias, **kw)
+    for _ in range(3): f()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): f()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    print(f'{name} M={M} N={N} K={K}: {us:7.1f} us  {2 * M * N * K / us / 1e6:7.1f} TFLOP/s')
