@@ -205,12 +205,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll 1
       for (int c0 = half * 32; c0 < ((p.debug & 1) ? 0 : BN); c0 += 64) {
         uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
-        tc::tmem_ld_wait();
+        if (!(p.debug & 4)) {
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = i;
+        }
         const int col0 = nt * BN + c0;
         if (p.tma_store) {
           if (kb1 > kb0 && col0 < p.N) {        // warp-uniform
-            if (lane == 0) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
+            if (lane == 0 && !(p.debug & 2)) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -237,7 +242,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             tc::fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.debug & 2)) {
               const int y = b * p.M + mt * BM + q * 32;
               if (p.accumulate) tc::tma_reduce_add_2d(&tma_c, my_stage, col0, y);
               else tc::tma_store_2d(&tma_c, my_stage, col0, y);

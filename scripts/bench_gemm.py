@@ -3,8 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from plankassembly_b200 import ops
-shapes = [('qkv  fwd', 32768, 1536, 512, {}), ('out  fwd', 32768, 512, 512, {}), ('ffn1 fwd', 32768, 1024, 512, {}), ('ffn2 fwd', 32768, 512, 1024, {}),
-          ('qkv  dX ', 32768, 512, 1536, {'b_mn': True}), ('qkv  dW ', 1536, 512, 32768, {'a_mn': True, 'b_mn': True, 'split_k': 6, 'accumulate': True})]
+shapes = [s for s in [('qkv  fwd', 32768, 1536, 512, {}), ('out  fwd', 32768, 512, 512, {}), ('ffn1 fwd', 32768, 1024, 512, {}), ('ffn2 fwd', 32768, 512, 1024, {}),
+          ('qkv  dX ', 32768, 512, 1536, {'b_mn': True}), ('qkv  dW ', 1536, 512, 32768, {'a_mn': True, 'b_mn': True, 'split_k': 6, 'accumulate': True})] if len(sys.argv) < 2 or sys.argv[1] in s[0]]
 for name, M, N, K, kw in shapes:
     if kw.get('a_mn'):
         a = torch.randn(K, M, device='cuda'); lda = M
