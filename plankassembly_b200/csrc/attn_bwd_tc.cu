@@ -221,9 +221,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int kk = c0 + c + e;
-              float v = __uint_as_float(rs[c + e]) * p.scale_log2 + bias_s[buf * C::BK + kk] - lse2;
+              float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, bias_s[buf * C::BK + kk] - lse2);
               if (diag && k0 + kk > qi) v = -INFINITY;
-              const float pr = exp2f(v);
+              const float pr = fast_exp2(v);
               const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dl);
               rs[c + e] = __float_as_uint(tf32_rn(ds));
             }
@@ -469,14 +469,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             float mk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
+            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);     // per-query stats, 4 columns at a time
+            const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
+            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int qq = c0 + c + e;
-              float v = __uint_as_float(rs[c + e]) * p.scale_log2 - lse2[qq];
+              float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, -lq[e]);
               if (!k_ok || (diag && kj > q0 + qq)) v = -INFINITY;
-              const float pr = exp2f(v);
+              const float pr = fast_exp2(v);
               const float pd = pr * mk[e];
-              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dl[qq]);
+              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dq4[e]);
               rs[c + e] = __float_as_uint(tf32_rn(pd));
               rd[c + e] = __float_as_uint(tf32_rn(ds));
             }

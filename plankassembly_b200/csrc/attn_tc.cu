@@ -30,7 +30,8 @@ template <int DH> struct Cfg {
   static constexpr int kOffV = kOffK + kKStages * kTileBytes;
   static constexpr int kOffBias = kOffV + kVStages * kTileBytes;
   static constexpr int kOffXch = kOffBias + 2 * BKV * 4;     // [2 bufs x 2 halves + 2][128] floats: max / sum exchange
-  static constexpr int kOffBar = kOffXch + 6 * BQ * 4;
+  static constexpr int kOffFlag = kOffXch + 6 * BQ * 4;
+  static constexpr int kOffBar = kOffFlag + 64;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColS = 0;                          // 2 x 128 columns  S / P
@@ -54,6 +55,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
   float* xch_s = reinterpret_cast<float*>(smem + C::kOffXch);
+  int* flag_s = reinterpret_cast<int*>(smem + C::kOffFlag);      // [2 bufs][4 warps]: all 32 keys valid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
@@ -229,6 +231,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const int kj = k0 + tid;
           const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
           bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
+          const bool all_ok = __all_sync(0xffffffffu, ok);
+          if (lane == 0) flag_s[buf * 4 + (tid >> 5)] = all_ok ? 1 : 0;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(s_full + buf, (sc >> 1) & 1);
@@ -244,23 +248,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           for (int c = 0; c < 32; ++c) s[c0 + c] = __uint_as_float(r[c]);
         }
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
-        float mx = -INFINITY;
+        // fast path: every key of the tile is valid and no causal boundary crosses it -> no per-element masking
+        const bool clean = !diag && (flag_s[buf * 4] & flag_s[buf * 4 + 1] & flag_s[buf * 4 + 2] & flag_s[buf * 4 + 3]);
+        float mx = -INFINITY;                  // running in the RAW score domain; scale folded into the exp2 FFMA
+        if (clean) {
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          float v = s[c] * p.scale_log2 + bias_s[buf * BKV + half * HC + c];
-          if (diag && k0 + half * HC + c > qi) v = -INFINITY;
-          s[c] = v;
-          mx = fmaxf(mx, v);
+          for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < HC; ++c) {
+            float v = s[c] + bias_s[buf * BKV + half * HC + c];
+            if (diag && k0 + half * HC + c > qi) v = -INFINITY;
+            s[c] = v;
+            mx = fmaxf(mx, v);
+          }
         }
         xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
         const float m_new = fmaxf(m_run, mx);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-        const float corr = exp2f(m_run - m_safe);
+        const float corr = fast_exp2((m_run - m_safe) * p.scale_log2);
+        const float neg_ms = -m_safe * p.scale_log2;
         float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < HC; ++c) { s[c] = exp2f(s[c] - m_safe); rs += s[c]; }
+        for (int c = 0; c < HC; ++c) { s[c] = fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs += s[c]; }
         l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
@@ -272,7 +284,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
           }
 #pragma unroll
-          for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] * ks : 0.f;
+          for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
         }
 #pragma unroll
         for (int c0 = 0; c0 < HC; c0 += 32) {
@@ -295,7 +307,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float l_tot = l_run + xch_s[(4 + (half ^ 1)) * BQ + row];
       if (qi < p.Lq) {
-        const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        const float inv = l_tot > 0.f ? ks / l_tot : 0.f;
         if (has_o) {
           float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + half * 32;
 #pragma unroll
@@ -306,7 +318,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
         if (p.lse != nullptr && half == 0)
-          p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
+          p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
     }
