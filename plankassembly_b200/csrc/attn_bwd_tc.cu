@@ -194,13 +194,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const float lse = q_ok ? p.lse[rg] : -INFINITY;
       const float lse2 = lse == -INFINITY ? INFINITY : lse * kLog2e;     // +inf => P = 0
       const float dl = q_ok ? p.delta[rg] : 0.f;
+      auto key_ok = [&](int k0n) {
+        const int kj = k0n + tid;
+        return kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+      };
+      bool ok_pref = tid < C::BK ? key_ok(0) : false;        // global loads run one tile ahead of their use
       for (int j = 0; j < n; ++j, ++sc) {
         const int buf = sc & 1, k0 = j * C::BK;
         if (tid < C::BK) {
-          const int kj = k0 + tid;
-          const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
-          bias_s[buf * C::BK + tid] = ok ? 0.f : -INFINITY;
+          bias_s[buf * C::BK + tid] = ok_pref ? 0.f : -INFINITY;
+          if (j + 1 < n) ok_pref = key_ok(k0 + C::BK);
         }
+        uint32_t mw = 0xffffffffu;                           // keep-bits of this thread's 32 keys for this query row
+        if (p.p_drop > 0.f) mw = (q_ok && ((k0 + half * 32) >> 5) < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + ((k0 + half * 32) >> 5)) : 0u;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(sdp_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
@@ -210,8 +216,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BK + c0, rd);
-          uint32_t mw = 0xffffffffu;                       // keep-bits of keys k0+c0 .. +31 for this query row
-          if (p.p_drop > 0.f) mw = (q_ok && ((k0 + c0) >> 5) < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + ((k0 + c0) >> 5)) : 0u;
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
@@ -437,17 +441,25 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       const bool k_ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
       const int64_t bh_rows = (int64_t)(b * p.H + h) * p.Lq;
       const int n = q_tiles_all - i0;
+      auto load_stat = [&](int q0n) -> float {   // lse (log2 domain; +inf kills the row) for tid < 64, delta for 64..127
+        const int q = q0n + (tid & 63);
+        if (tid < 64) {
+          const float l = q < p.Lq ? p.lse[bh_rows + q] : -INFINITY;
+          return l == -INFINITY ? INFINITY : l * kLog2e;
+        }
+        return q < p.Lq ? p.delta[bh_rows + q] : 0.f;
+      };
+      float stat_pref = (tid < 128 && n > 0) ? load_stat(i0 * C::BQ) : 0.f;   // global loads run one tile ahead
       for (int j = 0; j < n; ++j, ++sc) {
         const int buf = sc & 1, q0 = (i0 + j) * C::BQ;
-        {  // per-query statistics of this tile: lse (log2 domain; +inf kills the row) and delta
-          const int q = q0 + (tid & 63);
-          if (tid < 64) {
-            float l = q < p.Lq ? p.lse[bh_rows + q] : -INFINITY;
-            stat_s[buf * 128 + tid] = l == -INFINITY ? INFINITY : l * kLog2e;
-          } else if (tid < 128) {
-            stat_s[buf * 128 + tid] = q < p.Lq ? p.delta[bh_rows + q] : 0.f;
-          }
+        if (tid < 128) {
+          stat_s[buf * 128 + tid] = stat_pref;
+          if (j + 1 < n) stat_pref = load_stat(q0 + C::BQ);
         }
+        uint32_t mw = 0xffffffffu;              // keep-bits of this thread's 32 queries for this key (column plane)
+        if (p.p_drop > 0.f)
+          mw = (kj < p.LkW * 32 && ((q0 + half * 32) >> 5) < p.LqW)
+                   ? __ldg(p.drop_cols + ((int64_t)(b * p.H + h) * (p.LkW * 32) + kj) * p.LqW + ((q0 + half * 32) >> 5)) : 0u;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(st_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
@@ -459,10 +471,6 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
-          uint32_t mw = 0xffffffffu;                       // keep-bits of queries q0+c0 .. +31 for this key (column plane)
-          if (p.p_drop > 0.f)
-            mw = (kj < p.LkW * 32 && ((q0 + c0) >> 5) < p.LqW)
-                     ? __ldg(p.drop_cols + ((int64_t)(b * p.H + h) * (p.LkW * 32) + kj) * p.LqW + ((q0 + c0) >> 5)) : 0u;
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {

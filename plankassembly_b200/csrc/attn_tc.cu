@@ -224,28 +224,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ++oc;
       };
 
+      // Global loads on this path (key-padding bytes, dropout words) are issued a tile ahead / at the top of the
+      // tile so that their ~700-cycle latency never sits on the per-tile dependent chain.
+      auto key_ok = [&](int k0n) {
+        const int kj = k0n + tid;
+        return kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+      };
+      bool ok_pref = tid < BKV ? key_ok(0) : false;
       for (int j = 0; j < n; ++j) {
         const int buf = sc & 1;
         const int k0 = j * BKV;
         if (tid < BKV) {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
-          const int kj = k0 + tid;
-          const bool ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+          const bool ok = ok_pref;
           bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
           const bool all_ok = __all_sync(0xffffffffu, ok);
           if (lane == 0) flag_s[buf * 4 + (tid >> 5)] = all_ok ? 1 : 0;
+          if (j + 1 < n) ok_pref = key_ok(k0 + BKV);
+        }
+        uint32_t w[HC / 32];                   // keep-bits of this row's 64 keys (precomputed Philox bit plane)
+        if (p.p_drop > 0.f) {
+#pragma unroll
+          for (int i = 0; i < HC / 32; ++i) {
+            const int wi = ((k0 + half * HC) >> 5) + i;
+            w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
+          }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(s_full + buf, (sc >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + half * HC;
         float s[HC];
-#pragma unroll
-        for (int c0 = 0; c0 < HC; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(s_addr + c0, r);
+        {
+          uint32_t r0[32], r1[32];               // both 32-column chunks in flight before the single wait
+          tc::tmem_ld_32x32(s_addr, r0);
+          tc::tmem_ld_32x32(s_addr + 32, r1);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) s[c0 + c] = __uint_as_float(r[c]);
+          for (int c = 0; c < 32; ++c) { s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]); }
         }
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
         // fast path: every key of the tile is valid and no causal boundary crosses it -> no per-element masking
@@ -276,13 +291,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
-          // keep-bits of this row's 64 keys: 2 words of the precomputed Philox bit plane (dropmask.cu)
-          uint32_t w[HC / 32];
-#pragma unroll
-          for (int i = 0; i < HC / 32; ++i) {
-            const int wi = ((k0 + half * HC) >> 5) + i;
-            w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
-          }
 #pragma unroll
           for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
         }
