@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
@@ -44,6 +46,7 @@ struct Params {
   float scale_log2;   // scale * log2(e)
   float p_drop; const uint32_t* drop_rows; int LkW;
   int q_tiles, items;
+  int debug;          // ablation bits for timing experiments (PLANK_B200_ATTN_DEBUG); 0 in production
 };
 
 template <int DH>
@@ -211,7 +214,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int obuf = oc & 1;
         tc::mbar_wait(o_full + obuf, (oc >> 1) & 1);
         tc::tc_fence_after();
-        if (has_o) {
+        if (has_o && !(p.debug & 4)) {
           uint32_t r[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColO + obuf * DH + half * 32, r);
           tc::tmem_ld_wait();
@@ -256,9 +259,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         float s[HC];
         {
           uint32_t r0[32], r1[32];               // both 32-column chunks in flight before the single wait
-          tc::tmem_ld_32x32(s_addr, r0);
-          tc::tmem_ld_32x32(s_addr + 32, r1);
-          tc::tmem_ld_wait();
+          if (!(p.debug & 32)) {
+            tc::tmem_ld_32x32(s_addr, r0);
+            tc::tmem_ld_32x32(s_addr + 32, r1);
+            tc::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { r0[c] = 0x3f800000u + c; r1[c] = 0x3f800000u; }
+          }
 #pragma unroll
           for (int c = 0; c < 32; ++c) { s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]); }
         }
@@ -278,22 +286,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             mx = fmaxf(mx, v);
           }
         }
-        xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
+        if (!(p.debug & 8)) {
+          xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
+        }
         const float m_new = fmaxf(m_run, mx);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float corr = fast_exp2((m_run - m_safe) * p.scale_log2);
         const float neg_ms = -m_safe * p.scale_log2;
         float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < HC; ++c) { s[c] = fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs += s[c]; }
+        for (int c = 0; c < HC; ++c) { s[c] = (p.debug & 1) ? fmaf(s[c], p.scale_log2, neg_ms) : fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs += s[c]; }
         l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
 #pragma unroll
           for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
         }
+        if (!(p.debug & 2)) {
 #pragma unroll
         for (int c0 = 0; c0 < HC; c0 += 32) {
           uint32_t r[32];
@@ -302,6 +313,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tc::tmem_st_32x32(s_addr + c0, r);
         }
         tc::tmem_st_wait();
+        } else if (rs == 123.f) { p.o[0] = s[1]; }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(p_full + buf);
@@ -355,6 +367,7 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
     pa_set_error("pa_attn_fwd (tc): p_drop > 0 needs drop_rows from pa_dropout_mask");
     return PA_ERR_ARG;
   }
+  { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.q_tiles = (a.Lq + BQ - 1) / BQ;
   p.items = p.q_tiles * a.H * a.B;
   auto kern = attn_fwd_tc_kernel<DH>;
