@@ -193,6 +193,10 @@ int pa_decode_head(const float* h, const float* lv, const float* pf, const float
                    int64_t Tmax, int B, int d, int V, int t, const int* t_dev, int end_token, int64_t* samples,
                    int64_t* attach, int64_t ld, int32_t* first_end, void* stream);
 
+/* Debug: per-role barrier wait cycles of CTA 0 of the last tensor-core attention forward that ran with
+ * PLANK_B200_ATTN_DEBUG bit 64 set (32 counters, see attn_tc.cu). */
+int pa_debug_attn_prof(unsigned long long* out32_host);
+
 #ifdef __cplusplus
 }
 #endif

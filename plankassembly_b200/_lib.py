@@ -54,6 +54,7 @@ SIGNATURES = {
     'pa_dropout_mask_words': (sz, [i32, i32, i32, i32]),
     'pa_dropout_mask': (i32, [vp, vp, i32, i32, i32, f32, u64, u64, vp]),
     'pa_attn_fwd': (i32, [C.POINTER(AttnFwdArgs), vp]),
+    'pa_debug_attn_prof': (i32, [vp]),
     'pa_attn_bwd': (i32, [C.POINTER(AttnBwdArgs), vp]),
     'pa_gemm_tf32': (i32, [C.POINTER(GemmArgs), vp]),
     'pa_dist_loss_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),

@@ -18,7 +18,17 @@
 
 #include <stdlib.h>
 
+// Wait-time profile of block 0 (cycles spent in each mbarrier / named-barrier wait, per role); filled only when
+// PLANK_B200_ATTN_DEBUG has bit 64 set, read back with pa_debug_attn_prof().
+__device__ unsigned long long g_attn_prof[32];
+
 namespace {
+
+#define TIMED_WAIT(slot, stmt)                                             \
+  do {                                                                     \
+    if (prof_on) { long long t0__ = clock64(); stmt; prof[slot] += clock64() - t0__; } \
+    else { stmt; }                                                         \
+  } while (0)
 
 constexpr int BQ = 128, BKV = 128;
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two warpgroups)
@@ -73,6 +83,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool prof_on = (p.debug & 64) && blockIdx.x == 0;
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_kernel0 = clock64();
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
     tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
@@ -106,20 +119,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         item_coords(item, b, h, q0, n);
-        tc::mbar_wait(q_empty, (ic & 1) ^ 1);
+        TIMED_WAIT(0, tc::mbar_wait(q_empty, (ic & 1) ^ 1));
         tc::mbar_arrive_expect_tx(q_full, C::kTileBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) tc::tma_load_2d(smem + C::kOffQ + c * (BQ * 128), &tm_q, h * DH + c * 32, b * p.Lq + q0, q_full);
         for (int j = 0; j < n; ++j) {
           const int ks = kc % kKStages;
-          tc::mbar_wait(k_empty + ks, ((kc / kKStages) & 1) ^ 1);
+          TIMED_WAIT(1, tc::mbar_wait(k_empty + ks, ((kc / kKStages) & 1) ^ 1));
           tc::mbar_arrive_expect_tx(k_full + ks, C::kTileBytes);
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c)
             tc::tma_load_2d(smem + C::kOffK + ks * C::kTileBytes + c * (BKV * 128), &tm_k, h * DH + c * 32, b * p.Lk + j * BKV, k_full + ks);
           ++kc;
           const int vs = vc % kVStages;
-          tc::mbar_wait(v_empty + vs, ((vc / kVStages) & 1) ^ 1);
+          TIMED_WAIT(2, tc::mbar_wait(v_empty + vs, ((vc / kVStages) & 1) ^ 1));
           tc::mbar_arrive_expect_tx(v_full + vs, C::kTileBytes);
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c)
@@ -137,7 +150,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t sq = tc::smem_u32(smem + C::kOffQ);
       auto issue_qk = [&]() {
         const int ks = kc % kKStages;
-        tc::mbar_wait(k_full + ks, (kc / kKStages) & 1);
+        TIMED_WAIT(1, tc::mbar_wait(k_full + ks, (kc / kKStages) & 1));
         tc::tc_fence_after();
         const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes);
         const uint32_t d_tmem = tmem_base + C::kColS + (st & 1) * BKV;
@@ -156,17 +169,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         item_coords(item, b, h, q0, n);
-        tc::mbar_wait(q_full, ic & 1);
+        TIMED_WAIT(0, tc::mbar_wait(q_full, ic & 1));
         tc::tc_fence_after();
         issue_qk();
         if (n > 1) issue_qk();
         if (n <= 2) tc::tc_commit(q_empty);
         for (int j = 0; j < n; ++j) {
           const int buf = pt & 1;
-          tc::mbar_wait(p_full + buf, (pt >> 1) & 1);
-          tc::mbar_wait(o_empty + buf, ((pt >> 1) & 1) ^ 1);
+          TIMED_WAIT(2, tc::mbar_wait(p_full + buf, (pt >> 1) & 1));
+          TIMED_WAIT(3, tc::mbar_wait(o_empty + buf, ((pt >> 1) & 1) ^ 1));
           const int vs = vc % kVStages;
-          tc::mbar_wait(v_full + vs, (vc / kVStages) & 1);
+          TIMED_WAIT(4, tc::mbar_wait(v_full + vs, (vc / kVStages) & 1));
           tc::tc_fence_after();
           const uint32_t sv = tc::smem_u32(smem + C::kOffV + vs * C::kTileBytes);
           // V tile: kChunks MN blocks (32 head-dim columns each) of 128 key rows x 128 B; 4-row swizzle atoms
@@ -212,7 +225,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
       auto accumulate_o = [&]() {
         const int obuf = oc & 1;
-        tc::mbar_wait(o_full + obuf, (oc >> 1) & 1);
+        TIMED_WAIT(3, tc::mbar_wait(o_full + obuf, (oc >> 1) & 1));
         tc::tc_fence_after();
         if (has_o && !(p.debug & 4)) {
           uint32_t r[32];
@@ -252,8 +265,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        tc::mbar_wait(s_full + buf, (sc >> 1) & 1);
+        TIMED_WAIT(0, asm volatile("bar.sync 1, 256;" ::: "memory"));
+        TIMED_WAIT(1, tc::mbar_wait(s_full + buf, (sc >> 1) & 1));
         tc::tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + half * HC;
         float s[HC];
@@ -288,7 +301,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         if (!(p.debug & 8)) {
           xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          TIMED_WAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));
           mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
         }
         const float m_new = fmaxf(m_run, mx);
@@ -343,6 +356,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
     }
   }
+  if (prof_on && lane == 0 && warp <= 2) {
+    for (int i = 0; i < 8; ++i) g_attn_prof[warp * 8 + i] = (unsigned long long)prof[i];
+    if (warp == 2) g_attn_prof[31] = (unsigned long long)(clock64() - t_kernel0);
+  }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -392,4 +409,10 @@ int pa_attn_fwd_tc(const pa_attn_fwd_args* a, void* stream) {
     case 64: return launch<64>(*a, (cudaStream_t)stream);
     default: pa_set_error("pa_attn_fwd (tc): head dim %d unsupported (32, 64)", a->dh); return PA_ERR_UNSUPPORTED;
   }
+}
+
+// debug only (not part of the documented ABI surface used by the model): copy the wait-time profile to the host
+extern "C" int pa_debug_attn_prof(unsigned long long* out32_host) {
+  PA_CUDA(cudaMemcpyFromSymbol(out32_host, g_attn_prof, sizeof(unsigned long long) * 32));
+  return PA_OK;
 }

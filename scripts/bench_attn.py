@@ -36,3 +36,14 @@ _lib.PROFILE_HOOK = None
 t_b = sum(a.elapsed_time(b) for a, b in ev) / len(ev) * 1e3
 fl = 4 * B * H * L * L * dh
 print(f'p_drop={p} debug={os.environ.get("PLANK_B200_ATTN_DEBUG", "0")}: fwd {t_f:7.1f} us ({fl / t_f / 1e6:6.1f} TFLOP/s)   bwd(delta+dq+dkdv) {t_b:7.1f} us ({2.5 * fl / t_b / 1e6:6.1f} TFLOP/s)')
+if int(os.environ.get('PLANK_B200_ATTN_DEBUG', '0')) & 64:
+    import ctypes
+    buf = (ctypes.c_ulonglong * 32)()
+    fwd(); torch.cuda.synchronize()
+    _lib.load().pa_debug_attn_prof(buf)
+    v = list(buf)
+    tot = v[31]
+    print(f'CTA0 kernel cycles {tot}')
+    print('producer waits: q_empty %5.1f%%  k_empty %5.1f%%  v_empty %5.1f%%' % tuple(100 * x / tot for x in v[0:3]))
+    print('mma waits     : q_full %5.1f%%  k_full %5.1f%%  p_full %5.1f%%  o_empty %5.1f%%  v_full %5.1f%%' % tuple(100 * x / tot for x in v[8:13]))
+    print('softmax waits : bar(bias) %5.1f%%  s_full %5.1f%%  bar(max) %5.1f%%  o_full %5.1f%%' % tuple(100 * x / tot for x in v[16:20]))
