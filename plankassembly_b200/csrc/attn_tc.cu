@@ -72,15 +72,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;            // [3]
-  uint64_t* k_empty = bars + 5;           // [3]
-  uint64_t* v_full = bars + 8;            // [2]
-  uint64_t* v_empty = bars + 10;          // [2]
-  uint64_t* s_full = bars + 12;           // [2]
-  uint64_t* p_full = bars + 14;           // [2]
-  uint64_t* o_full = bars + 16;           // [2]
-  uint64_t* o_empty = bars + 18;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* k_full = bars + 2;            // [<= 3]
+  uint64_t* k_empty = bars + 5;           // [<= 3]
+  uint64_t* v_full = bars + 8;            // [<= 3]
+  uint64_t* v_empty = bars + 11;          // [<= 3]
+  uint64_t* s_full = bars + 14;           // [2]
+  uint64_t* p_full = bars + 16;           // [2]
+  uint64_t* o_full = bars + 18;           // [2]
+  uint64_t* o_empty = bars + 20;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool prof_on = (p.debug & 64) && blockIdx.x == 0;

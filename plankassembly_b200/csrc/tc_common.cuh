@@ -38,7 +38,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 50000000u) {
+    if (++spins > 4000000u) {
       printf("plank_b200: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
