@@ -23,26 +23,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~the hint (ns)
-// elapses.  Without the hint a waiting thread re-polls every ~17 cycles, and the single-thread TMA / MMA roles
-// (which wait most of the time) then burn about half of their scheduler's issue slots -- stolen from the
-// elementwise warps that share the scheduler.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a wrong barrier protocol must surface as a trap, never as a hung GPU.
+// Bounded spin: a wrong barrier protocol must surface as a trap, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 400000u) {
+    if (++spins > 4000000u) {
       printf("plank_b200: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
