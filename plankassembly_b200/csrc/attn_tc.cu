@@ -7,9 +7,9 @@
 //   O_j = P V   : tcgen05.mma with A = P straight from TMEM, B = V tile (smem, MN-major, 128B_BASE32B)
 //   O += O_j    : rescaled accumulation in registers (no TMEM read-modify-write of O)
 //
-// Persistent CTAs (one per SM), 64 + 128*NW threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// then NW (= 4) softmax/accumulate warpgroups (each: 128 threads = 128 query rows = 128 TMEM lanes, owning one
-// column group of every score tile and of O).
+// Persistent CTAs (one per SM), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = two softmax/accumulate warpgroups (each: 128 threads = 128 query rows = 128 TMEM lanes,
+// owning one half of the key columns of every tile and one half of the head-dim columns of O).
 // Pipelines: K ring (3 stages) and V ring (2 stages) fed by TMA; S/P and O double-buffered in TMEM so
 // QK^T of tile j+1 and P V of tile j overlap the softmax of tile j.
 //   Reference: torch nn/functional.py multi_head_attention_forward as reached from ref models.py:206,212.
@@ -31,8 +31,7 @@ namespace {
   } while (0)
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int NW = 4;              // softmax warpgroups (column groups of every score tile)
-constexpr int kThreads = 64 + 128 * NW;   // warp 0 TMA, warp 1 MMA, then NW softmax warpgroups
+constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two warpgroups)
 constexpr int kKStages = 3, kVStages = 2;
 
 template <int DH> struct Cfg {
@@ -42,8 +41,8 @@ template <int DH> struct Cfg {
   static constexpr int kOffK = kTileBytes;
   static constexpr int kOffV = kOffK + kKStages * kTileBytes;
   static constexpr int kOffBias = kOffV + kVStages * kTileBytes;
-  static constexpr int kOffXch = kOffBias + 2 * BKV * 4;     // [2 bufs x NW groups + NW][128] floats: max / sum exchange
-  static constexpr int kOffFlag = kOffXch + 3 * NW * BQ * 4;
+  static constexpr int kOffXch = kOffBias + 2 * BKV * 4;     // [2 bufs x 2 halves + 2][128] floats: max / sum exchange
+  static constexpr int kOffFlag = kOffXch + 6 * BQ * 4;
   static constexpr int kOffBar = kOffFlag + 64;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   static constexpr int kTmemCols = 512;
@@ -93,8 +92,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int s = 0; s < kKStages; ++s) { tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1); }
     for (int s = 0; s < kVStages; ++s) { tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 1); }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 4 * NW);
-      tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 4 * NW);
+      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 8);
+      tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 8);
     }
     tc::fence_barrier_init();
   }
@@ -201,19 +200,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else {
-    // ============================ softmax / accumulate: NW warpgroups ============================
-    // Warps w, w+4, w+8, ... share a TMEM lane quarter; warpgroup `grp` owns key columns [HC*grp, HC*grp+HC) of
-    // every 128-key tile and head-dim columns [OC*grp, OC*grp+OC) of O.  More warps per scheduler = the dependent
-    // per-tile chain (barrier -> tcgen05.ld -> exp2 -> tcgen05.st -> arrive) of one warp is hidden by the others.
-    // Row maxima are exchanged through smem once per tile; each group keeps a partial row sum.
+    // ============================ softmax / accumulate: two warpgroups ============================
+    // Warps 2..5 and 6..9 share TMEM lane quarters pairwise; warpgroup `half` owns key columns
+    // [64*half, 64*half+64) of every 128-key tile and head-dim columns [32*half, 32*half+32) of O.
+    // Row maxima are exchanged through smem once per tile; each half keeps a partial row sum.
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int tid = threadIdx.x - 64;                    // 0 .. 128*NW-1
+    const int tid = threadIdx.x - 64;                    // 0..255
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    constexpr int HC = BKV / NW;                         // score columns per group (32)
-    constexpr int OC = DH / NW;                          // O columns per group (16 or 8)
+    constexpr int HC = BKV / 2;                          // score columns per half
+    const bool has_o = half * 32 < DH;
     uint32_t sc = 0, oc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, q0, n;
@@ -221,20 +219,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int qi = q0 + row;
       const int64_t row_global = ((int64_t)(b * p.H + h) * p.Lq + qi);
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-      float o_acc[OC];
+      float o_acc[32];
 #pragma unroll
-      for (int c = 0; c < OC; ++c) o_acc[c] = 0.f;
+      for (int c = 0; c < 32; ++c) o_acc[c] = 0.f;
 
       auto accumulate_o = [&]() {
         const int obuf = oc & 1;
         TIMED_WAIT(3, tc::mbar_wait(o_full + obuf, (oc >> 1) & 1));
         tc::tc_fence_after();
-        if (!(p.debug & 4)) {
-          uint32_t r[OC];
-          tc::tmem_ld_cols<OC>(tmem_base + lane_addr + C::kColO + obuf * DH + grp * OC, r);
+        if (has_o && !(p.debug & 4)) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColO + obuf * DH + half * 32, r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < OC; ++c) o_acc[c] = o_acc[c] * corr_prev + __uint_as_float(r[c]);
+          for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_prev + __uint_as_float(r[c]);
         }
         tc::tc_fence_before();
         __syncwarp();
@@ -243,7 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       };
 
       // Global loads on this path (key-padding bytes, dropout words) are issued a tile ahead / at the top of the
-      // tile so that their latency never sits on the per-tile dependent chain.
+      // tile so that their ~700-cycle latency never sits on the per-tile dependent chain.
       auto key_ok = [&](int k0n) {
         const int kj = k0n + tid;
         return kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
@@ -259,27 +257,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (lane == 0) flag_s[buf * 4 + (tid >> 5)] = all_ok ? 1 : 0;
           if (j + 1 < n) ok_pref = key_ok(k0 + BKV);
         }
-        uint32_t w = 0xffffffffu;              // keep-bits of this row's 32 keys (precomputed Philox bit plane)
+        uint32_t w[HC / 32];                   // keep-bits of this row's 64 keys (precomputed Philox bit plane)
         if (p.p_drop > 0.f) {
-          const int wi = (k0 >> 5) + grp;
-          w = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
+#pragma unroll
+          for (int i = 0; i < HC / 32; ++i) {
+            const int wi = ((k0 + half * HC) >> 5) + i;
+            w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
+          }
         }
-        TIMED_WAIT(0, asm volatile("bar.sync 1, %0;" ::"n"(128 * NW) : "memory"));
+        TIMED_WAIT(0, asm volatile("bar.sync 1, 256;" ::: "memory"));
         TIMED_WAIT(1, tc::mbar_wait(s_full + buf, (sc >> 1) & 1));
         tc::tc_fence_after();
-        const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + grp * HC;
+        const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + half * HC;
         float s[HC];
         {
-          uint32_t r0[32];
+          uint32_t r0[32], r1[32];               // both 32-column chunks in flight before the single wait
           if (!(p.debug & 32)) {
             tc::tmem_ld_32x32(s_addr, r0);
+            tc::tmem_ld_32x32(s_addr + 32, r1);
             tc::tmem_ld_wait();
           } else {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) r0[c] = 0x3f800000u + c;
+            for (int c = 0; c < 32; ++c) { r0[c] = 0x3f800000u + c; r1[c] = 0x3f800000u; }
           }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) s[c] = __uint_as_float(r0[c]);
+          for (int c = 0; c < 32; ++c) { s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]); }
         }
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
         // fast path: every key of the tile is valid and no causal boundary crosses it -> no per-element masking
@@ -291,17 +293,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         } else {
 #pragma unroll
           for (int c = 0; c < HC; ++c) {
-            float v = s[c] + bias_s[buf * BKV + grp * HC + c];
-            if (diag && k0 + grp * HC + c > qi) v = -INFINITY;
+            float v = s[c] + bias_s[buf * BKV + half * HC + c];
+            if (diag && k0 + half * HC + c > qi) v = -INFINITY;
             s[c] = v;
             mx = fmaxf(mx, v);
           }
         }
         if (!(p.debug & 8)) {
-          xch_s[(buf * NW + grp) * BQ + row] = mx;          // exchange the per-group row maxima
-          TIMED_WAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(128 * NW) : "memory"));
-#pragma unroll
-          for (int g = 0; g < NW; ++g) mx = fmaxf(mx, xch_s[(buf * NW + g) * BQ + row]);
+          xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
+          TIMED_WAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));
+          mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
         }
         const float m_new = fmaxf(m_run, mx);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
@@ -310,18 +311,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         float rs = 0.f;
 #pragma unroll
         for (int c = 0; c < HC; ++c) { s[c] = (p.debug & 1) ? fmaf(s[c], p.scale_log2, neg_ms) : fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs += s[c]; }
-        l_run = l_run * corr + rs;                        // partial sum over this group's columns
+        l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
 #pragma unroll
-          for (int c = 0; c < HC; ++c) s[c] = ((w >> c) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
+          for (int c = 0; c < HC; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
         }
         if (!(p.debug & 2)) {
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(tf32_rn(s[c]));
-          tc::tmem_st_32x32(s_addr, r);
-          tc::tmem_st_wait();
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(tf32_rn(s[c0 + c]));
+          tc::tmem_st_32x32(s_addr + c0, r);
+        }
+        tc::tmem_st_wait();
         } else if (rs == 123.f) { p.o[0] = s[1]; }
         tc::tc_fence_before();
         __syncwarp();
@@ -331,25 +335,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         corr_prev = corr;
       }
       accumulate_o();
-      // total row sum = sum of the groups' partial sums
-      xch_s[(2 * NW + grp) * BQ + row] = l_run;
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * NW) : "memory");
-      float l_tot = 0.f;
-#pragma unroll
-      for (int g = 0; g < NW; ++g) l_tot += xch_s[(2 * NW + g) * BQ + row];
+      // total row sum = sum of the two halves' partial sums
+      xch_s[(4 + half) * BQ + row] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float l_tot = l_run + xch_s[(4 + (half ^ 1)) * BQ + row];
       if (qi < p.Lq) {
         const float inv = l_tot > 0.f ? ks / l_tot : 0.f;
-        float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + grp * OC;
+        if (has_o) {
+          float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + half * 32;
 #pragma unroll
-        for (int c = 0; c < OC; c += 4) {
-          float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-          if (p.round_out) v = tf32_rn4(v);
-          *reinterpret_cast<float4*>(op + c) = v;
+          for (int c = 0; c < 32; c += 4) {
+            float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+            if (p.round_out) v = tf32_rn4(v);
+            *reinterpret_cast<float4*>(op + c) = v;
+          }
         }
-        if (p.lse != nullptr && grp == 0)
+        if (p.lse != nullptr && half == 0)
           p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * NW) : "memory");      // xch_s (row sums) is reused by the next item
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
     }
   }
   if (prof_on && lane == 0 && warp <= 2) {
