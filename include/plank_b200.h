@@ -193,6 +193,56 @@ int pa_decode_head(const float* h, const float* lv, const float* pf, const float
                    int64_t Tmax, int B, int d, int V, int t, const int* t_dev, int end_token, int64_t* samples,
                    int64_t* attach, int64_t ld, int32_t* first_end, void* stream);
 
+/* ---- K12, fused: the WHOLE greedy decode loop (every step of every sequence, models.py:284-307) as one
+ * persistent cooperative kernel: per step 6 x [QKV proj, cached self-attention, out proj, residual+LN, q proj,
+ * cross-attention over the once-projected memory K/V, out proj, residual+LN, FFN, residual+LN], final LN, heads,
+ * eval distribution, sampling, END bookkeeping and the next input embedding, with grid-wide barriers between
+ * the phases and no host involvement.  All fp32.  The caller owns every buffer:
+ *   layers[l].self_k/self_v [B,T,d] (filled by the kernel), cross_kv [B,S,2d] (K | V of the encoder memory,
+ *   projected by the caller with multihead_attn.in_proj rows d..3d), w_heads [V+d+1, d] = vocab_head |
+ *   pointer_head | switch_head weights stacked (b_heads likewise), part = part_bytes = pa_decode_fused_workspace()
+ *   bytes, state = PA_DEC_STATE_INTS int32 (zeroed by the call; on return state[2] = number of steps executed =
+ *   the reference's output length, state[1] = sequences that emitted END, state[3] = last first-END step).
+ * chains: number of independent sub-batches the grid is divided into (0 = automatic), see decode_fused.cu.
+ * Outputs: samples/attach [B,T] (attach = -1 where the token was not copied), first_end [B], hfin [B,T,d]. */
+#define PA_MAX_DEC_LAYERS 8
+#define PA_MAX_DEC_CHAINS 8
+#define PA_DEC_STATE_INTS 16
+typedef struct {
+  const float *w_sqkv, *b_sqkv;    /* self_attn.in_proj_weight [3d,d], in_proj_bias [3d] */
+  const float *w_so, *b_so;        /* self_attn.out_proj */
+  const float *g1, *be1;           /* norm1 */
+  const float *w_cq, *b_cq;        /* multihead_attn.in_proj rows 0..d-1 (query projection) */
+  const float *w_co, *b_co;        /* multihead_attn.out_proj */
+  const float *g2, *be2;           /* norm2 */
+  const float *w_f1, *b_f1;        /* linear1 [ff,d] */
+  const float *w_f2, *b_f2;        /* linear2 [d,ff] */
+  const float *g3, *be3;           /* norm3 */
+  float* self_k; float* self_v;
+  const float* cross_kv;
+} pa_decode_layer;
+typedef struct {
+  int B, S, T, d, H, ff, V, L, dof, end_token;
+  float layer_eps, final_eps;
+  pa_decode_layer layers[PA_MAX_DEC_LAYERS];
+  const float *gf, *bf;            /* decoder.norm */
+  const float *w_heads, *b_heads;
+  const float *e_val, *e_coord, *e_pos;
+  const uint8_t* kpm;              /* [B,S], 1 = PAD memory key */
+  float* y; float* o;              /* [B,d] scratch rows */
+  float* part; int64_t part_bytes;
+  float* hfin;
+  int64_t* samples; int64_t* attach;
+  int32_t* first_end;
+  int32_t* state;
+  int chains;
+  int profile;                     /* != 0: CTA 0 accumulates nanoseconds per phase kind, read back with pa_debug_decode_prof */
+} pa_decode_fused_args;
+size_t pa_decode_fused_workspace(int B, int d, int ff, int V);
+int pa_decode_fused(const pa_decode_fused_args* args, void* stream);
+/* Debug: ns spent by CTA 0 of the last profiled pa_decode_fused in [gemm, self-attn, row, cross-attn, head, barriers, -, -]. */
+int pa_debug_decode_prof(unsigned long long* out8_host);
+
 /* Debug: per-role barrier wait cycles of CTA 0 of the last tensor-core attention forward that ran with
  * PLANK_B200_ATTN_DEBUG bit 64 set (32 counters, see attn_tc.cu). */
 int pa_debug_attn_prof(unsigned long long* out32_host);

@@ -35,6 +35,23 @@ class GemmArgs(C.Structure):
                 ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32), ('round_out', i32)]
 
 
+fp = C.c_void_p
+PA_MAX_DEC_LAYERS = 8
+
+
+class DecodeLayer(C.Structure):
+    _fields_ = [(n, fp) for n in ('w_sqkv', 'b_sqkv', 'w_so', 'b_so', 'g1', 'be1', 'w_cq', 'b_cq', 'w_co', 'b_co', 'g2', 'be2',
+                                  'w_f1', 'b_f1', 'w_f2', 'b_f2', 'g3', 'be3', 'self_k', 'self_v', 'cross_kv')]
+
+
+class DecodeFusedArgs(C.Structure):
+    _fields_ = [('B', i32), ('S', i32), ('T', i32), ('d', i32), ('H', i32), ('ff', i32), ('V', i32), ('L', i32), ('dof', i32),
+                ('end_token', i32), ('layer_eps', f32), ('final_eps', f32), ('layers', DecodeLayer * PA_MAX_DEC_LAYERS),
+                ('gf', fp), ('bf', fp), ('w_heads', fp), ('b_heads', fp), ('e_val', fp), ('e_coord', fp), ('e_pos', fp),
+                ('kpm', fp), ('y', fp), ('o', fp), ('part', fp), ('part_bytes', i64), ('hfin', fp), ('samples', fp),
+                ('attach', fp), ('first_end', fp), ('state', fp), ('chains', i32), ('profile', i32)]
+
+
 # name -> (restype, argtypes); mirrors include/plank_b200.h one to one
 SIGNATURES = {
     'pa_abi_version': (i32, []),
@@ -65,6 +82,9 @@ SIGNATURES = {
     'pa_decode_embed': (i32, [vp, i64, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]),
     'pa_decode_attn': (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp]),
     'pa_decode_head': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i32, vp, vp, i64, vp, vp]),
+    'pa_decode_fused_workspace': (sz, [i32, i32, i32, i32]),
+    'pa_decode_fused': (i32, [C.POINTER(DecodeFusedArgs), vp]),
+    'pa_debug_decode_prof': (i32, [vp]),
 }
 
 _lib = None

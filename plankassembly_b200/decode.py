@@ -25,6 +25,9 @@ import os
 import torch
 import torch.nn.functional as F
 
+import ctypes as C
+
+from . import _lib
 from ._lib import call
 
 
@@ -36,7 +39,13 @@ class GreedyDecoder:
     def __init__(self, model, poll=16):
         self.m = model
         self.poll = poll
-        self.use_graph = os.environ.get('PLANK_B200_DECODE_GRAPH', '1') == '1'
+        # 'graph' (default): one CUDA graph of ~100 small kernels per step; 'eager': the same kernels launched one by one;
+        # 'fused': the whole loop as ONE persistent cooperative kernel (csrc/decode_fused.cu) -- correct, but not yet
+        # faster than the graph at batch 64 (profiles/r1_decode_fused.md)
+        self.mode = os.environ.get('PLANK_B200_DECODE', 'graph')
+        if os.environ.get('PLANK_B200_DECODE_GRAPH', '1') != '1':
+            self.mode = 'eager'
+        self.use_graph = self.mode == 'graph'
         self._key = None
         self.graph = None
         self._lin_out = {}
@@ -61,7 +70,50 @@ class GreedyDecoder:
         self.attach = torch.empty(B, T, device=device, dtype=torch.int64)
         self.first_end = torch.empty(B, device=device, dtype=torch.int32)
         self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        self.state = torch.zeros(16, device=device, dtype=torch.int32)
+        ws = _lib.load().pa_decode_fused_workspace(B, d, m.decoder.layers[0].linear1.weight.shape[0], m.vocab_size)
+        self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
         self._key, self.graph = key, None
+
+    def _fused_args(self, B, S):
+        """Argument block of pa_decode_fused (raw device pointers of the canonical fp32 parameters)."""
+        m = self.m
+        d, T = m.num_model, m.max_output_length
+        a = _lib.DecodeFusedArgs()
+        a.B, a.S, a.T, a.d, a.H, a.ff, a.V, a.L = (B, S, T, d, m.num_head, m.decoder.layers[0].linear1.weight.shape[0], m.vocab_size,
+                                                  len(m.decoder.layers))
+        a.dof, a.end_token, a.layer_eps, a.final_eps = m.num_output_dof, m.token.END, float(m.layer_eps), 1e-5
+        keep = []                                    # tensors that must outlive the launch
+
+        def p(t):
+            t = t.detach()
+            if not t.is_contiguous():
+                t = t.contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        for li, l in enumerate(m.decoder.layers):
+            sa, ca, ly = l.self_attn, l.multihead_attn, a.layers[li]
+            ly.w_sqkv, ly.b_sqkv, ly.w_so, ly.b_so = p(sa.in_proj_weight), p(sa.in_proj_bias), p(sa.out_proj.weight), p(sa.out_proj.bias)
+            ly.g1, ly.be1, ly.g2, ly.be2, ly.g3, ly.be3 = (p(l.norm1.weight), p(l.norm1.bias), p(l.norm2.weight), p(l.norm2.bias),
+                                                           p(l.norm3.weight), p(l.norm3.bias))
+            ly.w_cq, ly.b_cq = p(ca.in_proj_weight), p(ca.in_proj_bias)          # rows 0..d-1 of the packed projection
+            ly.w_co, ly.b_co = p(ca.out_proj.weight), p(ca.out_proj.bias)
+            ly.w_f1, ly.b_f1, ly.w_f2, ly.b_f2 = p(l.linear1.weight), p(l.linear1.bias), p(l.linear2.weight), p(l.linear2.bias)
+            ly.self_k, ly.self_v, ly.cross_kv = self.self_k[li].data_ptr(), self.self_v[li].data_ptr(), self.cross_kv[li].data_ptr()
+        a.gf, a.bf = p(m.decoder.norm.weight), p(m.decoder.norm.bias)
+        # vocab | pointer-feature | switch heads as one [V+d+1, d] projection
+        a.w_heads = p(torch.cat([m.vocab_head.weight, m.pointer_head.weight, m.switch_head.weight], 0))
+        a.b_heads = p(torch.cat([m.vocab_head.bias, m.pointer_head.bias, m.switch_head.bias], 0))
+        a.e_val, a.e_coord, a.e_pos = (p(m.input_embeddings['input_value'].weight), p(m.query_coord_embedding.weight),
+                                       p(m.query_pos_embedding.weight))
+        a.kpm, a.y, a.o = self.kpm.data_ptr(), self.y.data_ptr(), self.o.data_ptr()
+        a.part, a.part_bytes = self.part.data_ptr(), self.part.numel() * 4
+        a.hfin, a.samples, a.attach = self.hfin.data_ptr(), self.samples.data_ptr(), self.attach.data_ptr()
+        a.first_end, a.state = self.first_end.data_ptr(), self.state.data_ptr()
+        a.chains = int(os.environ.get('PLANK_B200_DECODE_CHAINS', '0'))
+        a.profile = int(os.environ.get('PLANK_B200_DECODE_PROF', '0'))
+        return a, keep
 
     def _lin(self, x, W, b, key, relu=False):
         """y = x W^T + b in exact fp32 through pa_gemm_skinny_f32; outputs live in persistent buffers."""
@@ -144,6 +196,14 @@ class GreedyDecoder:
             ca = l.multihead_attn
             torch.addmm(ca.in_proj_bias[d:], mem2d, ca.in_proj_weight[d:].t(), out=self.cross_kv[li].view(B * S, 2 * d))
         self.kpm.copy_(in_kpm)
+        if self.mode == 'fused':
+            args, keep = self._fused_args(B, S)
+            call('pa_decode_fused', C.byref(args), _stream())
+            st = self.state[:4].tolist()                 # the one host sync of the whole decode
+            # the reference stops after the step at which every sequence has emitted END (ref models.py:306)
+            n_steps = st[3] + 1 if st[1] >= B else T
+            del keep
+            return self.samples[:, :n_steps].clone(), self.attach[:, :n_steps].clone()
         if self.use_graph and self.graph is None:
             self._capture()
         self.first_end.fill_(T)

@@ -81,8 +81,11 @@ def test_forward_returns_reference_shaped_dict():
     torch.mean(out['loss']); torch.mean(out['accuracy'])      # trainer_complete.py:66-67 does this
 
 
+@pytest.mark.parametrize('engine', ['graph', 'fused'])
 @pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init'])
-def test_greedy_decode_matches_reference(name):
+def test_greedy_decode_matches_reference(name, engine, monkeypatch):
+    """Both decode engines (CUDA graph of per-op kernels; one persistent cooperative kernel) against the reference's tokens."""
+    monkeypatch.setenv('PLANK_B200_DECODE', engine)
     cfg, sd, batch, g = case(name)
     m = build(cfg, sd).eval()
     out = m(to_dev(batch))
@@ -93,8 +96,10 @@ def test_greedy_decode_matches_reference(name):
     assert len(out['groundtruths']) == len(out['predicts']) == out['samples'].shape[0]
 
 
+@pytest.mark.parametrize('engine', ['graph', 'fused'])
 @pytest.mark.parametrize('ratio', [0, 5, 10, 20])
-def test_noisy_decode_matches_reference(ratio):
+def test_noisy_decode_matches_reference(ratio, engine, monkeypatch):
+    monkeypatch.setenv('PLANK_B200_DECODE', engine)
     cfg = syn.tiny_cfg()
     g = golden(f'tiny_trained_noise{ratio:02d}')
     batch = syn.batch_for(cfg, range(100, 108), noise_ratio=ratio / 100)
