@@ -18,6 +18,7 @@ LIB = os.path.join(CSRC, 'libplank_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+FLAGS += os.environ.get('PLANK_B200_NVCC_FLAGS', '').split()      # e.g. -DPA_ATTN_TRACE for the debug timeline
 
 
 def _digest(path, deps):

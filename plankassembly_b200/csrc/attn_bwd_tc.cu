@@ -122,7 +122,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues the MMAs.
+    {
       constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BQ, C::BK, 0, 0);
       constexpr uint32_t idesc_dq = tc::make_idesc_tf32(C::BQ, DH, 0, 1);
       uint32_t kc = 0, ic = 0, st = 0, dt = 0;
@@ -134,23 +135,26 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const uint32_t sk = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes);
         const uint32_t sv = sk + 2 * C::kKBytes;
         const int buf = st & 1;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t da = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
-          const uint64_t db = tc::make_smem_desc(sk + c * (C::BK * 128), 16, 1024);
+          for (int c = 0; c < C::kChunks; ++c) {
+            const uint64_t da = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
+            const uint64_t db = tc::make_smem_desc(sk + c * (C::BK * 128), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            const uint64_t da = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
+            const uint64_t db = tc::make_smem_desc(sv + c * (C::BK * 128), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::tc_commit(sdp_full + buf);
         }
-#pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t da = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
-          const uint64_t db = tc::make_smem_desc(sv + c * (C::BK * 128), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
-        }
-        tc::tc_commit(sdp_full + buf);
+        __syncwarp();
         ++st;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
@@ -162,21 +166,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         issue_sdp(kc);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_sdp(kc + 1);
-          if (j + 1 == n) tc::tc_commit(qdo_empty);      // all S/dP MMAs of this item are issued
+          if (j + 1 == n) { if (tc::elect_one()) tc::tc_commit(qdo_empty); __syncwarp(); }      // all S/dP MMAs of this item are issued
           const int buf = dt & 1;
           tc::mbar_wait(ds_full + buf, (dt >> 1) & 1);
           tc::tc_fence_after();
           const int s = kc % C::kStages;
           const uint32_t skm = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes + C::kKBytes);
           const uint64_t db = tc::make_smem_desc(skm, C::BK * 128, 512, tc::kLayoutSw128Base32);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < C::BK / 8; ++k)
-            tc::mma_tf32_ts(tmem_base + C::kColDQ, tmem_base + C::kColS + buf * C::BK + k * 8, tc::desc_advance(db, k * 1024), idesc_dq,
-                            (j > 0 || k > 0) ? 1u : 0u);
-          tc::tc_commit(kv_empty + s);
+            for (int k = 0; k < C::BK / 8; ++k)
+              tc::mma_tf32_ts(tmem_base + C::kColDQ, tmem_base + C::kColS + buf * C::BK + k * 8, tc::desc_advance(db, k * 1024), idesc_dq,
+                              (j > 0 || k > 0) ? 1u : 0u);
+            tc::tc_commit(kv_empty + s);
+            if (j + 1 == n) tc::tc_commit(dq_full);
+          }
+          __syncwarp();
           ++kc; ++dt;
         }
-        tc::tc_commit(dq_full);
       }
     }
   } else {
@@ -363,7 +370,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues the MMAs.
+    {
       constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BKV, C::BQ, 0, 0);      // [128 keys x 64 queries]
       constexpr uint32_t idesc_acc = tc::make_idesc_tf32(C::BKV, DH, 0, 1);       // [128 keys x DH]
       uint32_t qc = 0, ic = 0, st = 0, dt = 0;
@@ -375,23 +383,26 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         const uint32_t sq = tc::smem_u32(smem + C::kOffQ + s * C::kStageBytes);
         const uint32_t sdo = sq + 2 * C::kQBytes;
         const int buf = st & 1;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t da = tc::make_smem_desc(sk + c * (C::BKV * 128), 16, 1024);
-          const uint64_t db = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
+          for (int c = 0; c < C::kChunks; ++c) {
+            const uint64_t da = tc::make_smem_desc(sk + c * (C::BKV * 128), 16, 1024);
+            const uint64_t db = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            const uint64_t da = tc::make_smem_desc(sv + c * (C::BKV * 128), 16, 1024);
+            const uint64_t db = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::tc_commit(st_full + buf);
         }
-#pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t da = tc::make_smem_desc(sv + c * (C::BKV * 128), 16, 1024);
-          const uint64_t db = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
-        }
-        tc::tc_commit(st_full + buf);
+        __syncwarp();
         ++st;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
@@ -404,7 +415,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         if (n > 0) issue_st(qc);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_st(qc + 1);
-          if (j + 1 == n) tc::tc_commit(kv_empty);       // K_j / V_j no longer needed once these retire
+          if (j + 1 == n) { if (tc::elect_one()) tc::tc_commit(kv_empty); __syncwarp(); }       // K_j / V_j no longer needed once these retire
           const int buf = dt & 1;
           tc::mbar_wait(pds_full + buf, (dt >> 1) & 1);
           tc::tc_fence_after();
@@ -413,19 +424,25 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           const uint32_t sdom = sqm + 2 * C::kQBytes;
           const uint64_t dqm = tc::make_smem_desc(sqm, C::BQ * 128, 512, tc::kLayoutSw128Base32);
           const uint64_t ddom = tc::make_smem_desc(sdom, C::BQ * 128, 512, tc::kLayoutSw128Base32);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < C::BQ / 8; ++k)      // dV += P^T dO_i
-            tc::mma_tf32_ts(tmem_base + C::kColDV, tmem_base + C::kColS + buf * C::BQ + k * 8, tc::desc_advance(ddom, k * 1024), idesc_acc,
-                            (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < C::BQ / 8; ++k)      // dV += P^T dO_i
+              tc::mma_tf32_ts(tmem_base + C::kColDV, tmem_base + C::kColS + buf * C::BQ + k * 8, tc::desc_advance(ddom, k * 1024), idesc_acc,
+                              (j > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < C::BQ / 8; ++k)      // dK += dS^T Q_i
-            tc::mma_tf32_ts(tmem_base + C::kColDK, tmem_base + C::kColDP + buf * C::BQ + k * 8, tc::desc_advance(dqm, k * 1024), idesc_acc,
-                            (j > 0 || k > 0) ? 1u : 0u);
-          tc::tc_commit(q_empty + s);
+            for (int k = 0; k < C::BQ / 8; ++k)      // dK += dS^T Q_i
+              tc::mma_tf32_ts(tmem_base + C::kColDK, tmem_base + C::kColDP + buf * C::BQ + k * 8, tc::desc_advance(dqm, k * 1024), idesc_acc,
+                              (j > 0 || k > 0) ? 1u : 0u);
+            tc::tc_commit(q_empty + s);
+          }
+          __syncwarp();
           ++qc; ++dt;
         }
-        if (n == 0) tc::tc_commit(kv_empty);
-        tc::tc_commit(acc_full);
+        if (tc::elect_one()) {
+          if (n == 0) tc::tc_commit(kv_empty);
+          tc::tc_commit(acc_full);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -22,6 +22,24 @@
 // PLANK_B200_ATTN_DEBUG has bit 64 set, read back with pa_debug_attn_prof().
 __device__ unsigned long long g_attn_prof[32];
 
+// Build with PLANK_B200_NVCC_FLAGS=-DPA_ATTN_TRACE to record an event timeline of CTA 0 (clock64 per event and role:
+// 0 TMA producer, 1 MMA issuer, 2 softmax warp 2, 3 softmax warp 6), read back with pa_debug_attn_trace().
+#ifdef PA_ATTN_TRACE
+constexpr int kTraceLen = 1024;
+__device__ unsigned long long g_attn_trace[4][kTraceLen];
+__device__ int g_attn_trace_n[4];
+#define TRACE(role, ev)                                                                          \
+  do {                                                                                           \
+    if (trace_on && trace_n < kTraceLen) g_attn_trace[role][trace_n++] = ((unsigned long long)(ev) << 56) | (clock64() & 0xffffffffffffffull); \
+  } while (0)
+#define TRACE_DECL const bool trace_on = (p.debug & 1024) && blockIdx.x == 0; int trace_n = 0
+#define TRACE_END(role) do { if (trace_on) g_attn_trace_n[role] = trace_n; } while (0)
+#else
+#define TRACE(role, ev) do {} while (0)
+#define TRACE_DECL do {} while (0)
+#define TRACE_END(role) do {} while (0)
+#endif
+
 namespace {
 
 #define TIMED_WAIT(slot, stmt)                                             \
@@ -115,17 +133,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
+      TRACE_DECL;
       uint32_t kc = 0, vc = 0, ic = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         item_coords(item, b, h, q0, n);
         TIMED_WAIT(0, tc::mbar_wait(q_empty, (ic & 1) ^ 1));
+        TRACE(0, 0);
         tc::mbar_arrive_expect_tx(q_full, C::kTileBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) tc::tma_load_2d(smem + C::kOffQ + c * (BQ * 128), &tm_q, h * DH + c * 32, b * p.Lq + q0, q_full);
         for (int j = 0; j < n; ++j) {
           const int ks = kc % kKStages;
           TIMED_WAIT(1, tc::mbar_wait(k_empty + ks, ((kc / kKStages) & 1) ^ 1));
+          TRACE(0, 2);
           tc::mbar_arrive_expect_tx(k_full + ks, C::kTileBytes);
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c)
@@ -133,6 +154,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           ++kc;
           const int vs = vc % kVStages;
           TIMED_WAIT(2, tc::mbar_wait(v_empty + vs, ((vc / kVStages) & 1) ^ 1));
+          TRACE(0, 3);
           tc::mbar_arrive_expect_tx(v_full + vs, C::kTileBytes);
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c)
@@ -140,10 +162,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           ++vc;
         }
       }
+      TRACE_END(0);
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues.
+    {
+      TRACE_DECL;
       constexpr uint32_t idesc_qk = tc::make_idesc_tf32(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = tc::make_idesc_tf32(BQ, DH, 0, 1);
       uint32_t kc = 0, vc = 0, st = 0 /*QK tiles issued*/, pt = 0 /*PV tiles issued*/, ic = 0;
@@ -151,53 +176,69 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto issue_qk = [&]() {
         const int ks = kc % kKStages;
         TIMED_WAIT(1, tc::mbar_wait(k_full + ks, (kc / kKStages) & 1));
+        TRACE(1, 1);
         tc::tc_fence_after();
         const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes);
         const uint32_t d_tmem = tmem_base + C::kColS + (st & 1) * BKV;
+        if (tc::elect_one()) {
+          if (!(p.debug & 512))
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t dq = tc::make_smem_desc(sq + c * (BQ * 128), 16, 1024);
-          const uint64_t dk = tc::make_smem_desc(sk + c * (BKV * 128), 16, 1024);
+          for (int c = 0; c < C::kChunks; ++c) {
+            const uint64_t dq = tc::make_smem_desc(sq + c * (BQ * 128), 16, 1024);
+            const uint64_t dk = tc::make_smem_desc(sk + c * (BKV * 128), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(d_tmem, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc::mma_tf32_ss(d_tmem, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::tc_commit(k_empty + ks);
+          tc::tc_commit(s_full + (st & 1));
         }
-        tc::tc_commit(k_empty + ks);
-        tc::tc_commit(s_full + (st & 1));
+        __syncwarp();
+        TRACE(1, 2);
         ++kc; ++st;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         item_coords(item, b, h, q0, n);
         TIMED_WAIT(0, tc::mbar_wait(q_full, ic & 1));
+        TRACE(1, 0);
         tc::tc_fence_after();
         issue_qk();
         if (n > 1) issue_qk();
-        if (n <= 2) tc::tc_commit(q_empty);
+        if (n <= 2) { if (tc::elect_one()) tc::tc_commit(q_empty); __syncwarp(); }
         for (int j = 0; j < n; ++j) {
           const int buf = pt & 1;
           TIMED_WAIT(2, tc::mbar_wait(p_full + buf, (pt >> 1) & 1));
+          TRACE(1, 3);
           TIMED_WAIT(3, tc::mbar_wait(o_empty + buf, ((pt >> 1) & 1) ^ 1));
+          TRACE(1, 4);
           const int vs = vc % kVStages;
           TIMED_WAIT(4, tc::mbar_wait(v_full + vs, (vc / kVStages) & 1));
+          TRACE(1, 5);
           tc::tc_fence_after();
           const uint32_t sv = tc::smem_u32(smem + C::kOffV + vs * C::kTileBytes);
           // V tile: kChunks MN blocks (32 head-dim columns each) of 128 key rows x 128 B; 4-row swizzle atoms
           const uint64_t dv = tc::make_smem_desc(sv, BKV * 128, 512, tc::kLayoutSw128Base32);
           const uint32_t a_tmem = tmem_base + C::kColS + buf * BKV;
           const uint32_t d_tmem = tmem_base + C::kColO + buf * DH;
+          if (tc::elect_one()) {
+            if (!(p.debug & 256))
 #pragma unroll
-          for (int k = 0; k < BKV / 8; ++k)
-            tc::mma_tf32_ts(d_tmem, a_tmem + k * 8, tc::desc_advance(dv, k * 1024), idesc_pv, k > 0 ? 1u : 0u);
-          tc::tc_commit(v_empty + vs);
-          tc::tc_commit(o_full + buf);
+            for (int k = 0; k < BKV / 8; ++k)
+              tc::mma_tf32_ts(d_tmem, a_tmem + k * 8, tc::desc_advance(dv, k * 1024), idesc_pv, k > 0 ? 1u : 0u);
+            tc::tc_commit(v_empty + vs);
+            tc::tc_commit(o_full + buf);
+          }
+          __syncwarp();
+          TRACE(1, 6);
           ++vc; ++pt;
           if (j + 2 < n) {
             issue_qk();
-            if (j + 3 == n) tc::tc_commit(q_empty);      // that was the last QK^T of this item
+            if (j + 3 == n) { if (tc::elect_one()) tc::tc_commit(q_empty); __syncwarp(); }     // that was the last QK^T of this item
           }
         }
       }
+      TRACE_END(1);
     }
   } else {
     // ============================ softmax / accumulate: two warpgroups ============================
@@ -213,6 +254,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     constexpr int HC = BKV / 2;                          // score columns per half
     const bool has_o = half * 32 < DH;
     uint32_t sc = 0, oc = 0;
+#ifdef PA_ATTN_TRACE
+    const bool trace_on = (p.debug & 1024) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6);
+    int trace_n = 0;
+    const int trole = warp == 2 ? 2 : 3;
+#endif
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, q0, n;
       item_coords(item, b, h, q0, n);
@@ -226,6 +272,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto accumulate_o = [&]() {
         const int obuf = oc & 1;
         TIMED_WAIT(3, tc::mbar_wait(o_full + obuf, (oc >> 1) & 1));
+        TRACE(trole, 8);
         tc::tc_fence_after();
         if (has_o && !(p.debug & 4)) {
           uint32_t r[32];
@@ -237,6 +284,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(o_empty + obuf);
+        TRACE(trole, 9);
         ++oc;
       };
 
@@ -250,6 +298,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < n; ++j) {
         const int buf = sc & 1;
         const int k0 = j * BKV;
+        TRACE(trole, 0);
         if (tid < BKV) {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
           const bool ok = ok_pref;
           bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
@@ -266,7 +315,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
         }
         TIMED_WAIT(0, asm volatile("bar.sync 1, 256;" ::: "memory"));
+        TRACE(trole, 1);
         TIMED_WAIT(1, tc::mbar_wait(s_full + buf, (sc >> 1) & 1));
+        TRACE(trole, 2);
         tc::tc_fence_after();
         const uint32_t s_addr = tmem_base + lane_addr + C::kColS + buf * BKV + half * HC;
         float s[HC];
@@ -283,6 +334,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 32; ++c) { s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]); }
         }
+        TRACE(trole, 3);
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
         // fast path: every key of the tile is valid and no causal boundary crosses it -> no per-element masking
         const bool clean = !diag && (flag_s[buf * 4] & flag_s[buf * 4 + 1] & flag_s[buf * 4 + 2] & flag_s[buf * 4 + 3]);
@@ -304,6 +356,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           TIMED_WAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));
           mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
         }
+        TRACE(trole, 4);
         const float m_new = fmaxf(m_run, mx);
         const float m_safe = m_new == -INFINITY ? 0.f : m_new;
         const float corr = fast_exp2((m_run - m_safe) * p.scale_log2);
@@ -311,6 +364,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         float rs = 0.f;
 #pragma unroll
         for (int c = 0; c < HC; ++c) { s[c] = (p.debug & 1) ? fmaf(s[c], p.scale_log2, neg_ms) : fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs += s[c]; }
+        TRACE(trole, 5);
         l_run = l_run * corr + rs;                        // partial sum over this half's columns
         m_run = m_new;
         if (p.p_drop > 0.f) {
@@ -327,9 +381,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         tc::tmem_st_wait();
         } else if (rs == 123.f) { p.o[0] = s[1]; }
+        TRACE(trole, 6);
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(p_full + buf);
+        TRACE(trole, 7);
         ++sc;
         if (j > 0) accumulate_o();        // O_{j-1}: its P V overlapped this tile's softmax
         corr_prev = corr;
@@ -353,8 +409,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (p.lse != nullptr && half == 0)
           p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
       }
+      TRACE(trole, 10);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
+      TRACE(trole, 11);
     }
+#ifdef PA_ATTN_TRACE
+    if (trace_on) g_attn_trace_n[trole] = trace_n;
+#endif
   }
   if (prof_on && lane == 0 && warp <= 2) {
     for (int i = 0; i < 8; ++i) g_attn_prof[warp * 8 + i] = (unsigned long long)prof[i];
@@ -410,6 +471,14 @@ int pa_attn_fwd_tc(const pa_attn_fwd_args* a, void* stream) {
     default: pa_set_error("pa_attn_fwd (tc): head dim %d unsupported (32, 64)", a->dh); return PA_ERR_UNSUPPORTED;
   }
 }
+
+#ifdef PA_ATTN_TRACE
+extern "C" int pa_debug_attn_trace(unsigned long long* out_host /*[4][1024]*/, int* n_host /*[4]*/) {
+  PA_CUDA(cudaMemcpyFromSymbol(out_host, g_attn_trace, sizeof(unsigned long long) * 4 * kTraceLen));
+  PA_CUDA(cudaMemcpyFromSymbol(n_host, g_attn_trace_n, sizeof(int) * 4));
+  return PA_OK;
+}
+#endif
 
 // debug only (not part of the documented ABI surface used by the model): copy the wait-time profile to the host
 extern "C" int pa_debug_attn_prof(unsigned long long* out32_host) {
