@@ -146,7 +146,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and addresses) and one elected lane issues: inside a
+    // divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~70 cycles).
+    {
       constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -165,17 +167,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           // 32-wide MN block (BK rows x 128 B), SBO = 512 (4 K rows); one MMA (K=8) spans two K groups.
           const uint64_t da = A_MN ? tc::make_smem_desc(sa, BK * 128, 512, tc::kLayoutSw128Base32) : tc::make_smem_desc(sa, 16, 1024);
           const uint64_t db = B_MN ? tc::make_smem_desc(sb, BK * 128, 512, tc::kLayoutSw128Base32) : tc::make_smem_desc(sb, 16, 1024);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t dak = tc::desc_advance(da, A_MN ? k * 1024 : k * UK * 4);
-            const uint64_t dbk = tc::desc_advance(db, B_MN ? k * 1024 : k * UK * 4);
-            tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t dak = tc::desc_advance(da, A_MN ? k * 1024 : k * UK * 4);
+              const uint64_t dbk = tc::desc_advance(db, B_MN ? k * 1024 : k * UK * 4);
+              tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (CL > 1) tc::tc_commit_mcast(empty_bar + stage, 0x3);   // the slot is shared: both CTAs must be done with it
+            else tc::tc_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
+            if (kb + 1 == kb1) tc::tc_commit(tmem_full + acc);                  // accumulator complete -> epilogue
           }
-          if constexpr (CL > 1) tc::tc_commit_mcast(empty_bar + stage, 0x3);   // the slot is shared: both CTAs must be done with it
-          else tc::tc_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tc::tc_commit(tmem_full + acc);                // accumulator complete -> epilogue
+        if (kb0 >= kb1) { if (tc::elect_one()) tc::tc_commit(tmem_full + acc); __syncwarp(); }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
