@@ -23,6 +23,24 @@
 
 int pa_attn_delta_launch(const float* o, const float* d_o, int64_t ldo, int B, int H, int Lq, int dh, float* delta, cudaStream_t st);
 
+// Debug timeline (PLANK_B200_NVCC_FLAGS=-DPA_ATTN_TRACE, PLANK_B200_ATTN_DEBUG=1024): clock64 per event of CTA 0 of the
+// dQ kernel (roles: 0 TMA producer, 1 MMA issuer, 2 elementwise warp 2, 3 elementwise warp 6); pa_debug_attn_bwd_trace().
+#ifdef PA_ATTN_TRACE
+#include <stdlib.h>
+__device__ unsigned long long g_bwd_trace[4][1024];
+__device__ int g_bwd_trace_n[4];
+#define TRACE(role, ev)                                                                          \
+  do {                                                                                           \
+    if (trace_on && trace_n < 1024) g_bwd_trace[role][trace_n++] = ((unsigned long long)(ev) << 56) | (clock64() & 0xffffffffffffffull); \
+  } while (0)
+#define TRACE_DECL(cond) const bool trace_on = p.trace && blockIdx.x == 0 && (cond); int trace_n = 0
+#define TRACE_END(role) do { if (trace_on) g_bwd_trace_n[role] = trace_n; } while (0)
+#else
+#define TRACE(role, ev) do {} while (0)
+#define TRACE_DECL(cond) do {} while (0)
+#define TRACE_END(role) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 = two elementwise warpgroups (column halves)
@@ -36,6 +54,8 @@ struct BwdParams {
   float p_drop; const uint32_t* drop_rows; const uint32_t* drop_cols; int LkW, LqW;
   float* dbias;          // [3*H*DH] += column sums of dq | dk | dv (in-projection bias gradient), may be NULL
   int tiles, items;
+  int LkPad;             // keys rounded up to the key tile (per-item bias table length)
+  int trace;
 };
 
 // ================================================================================================
@@ -48,10 +68,12 @@ template <int DH> struct CfgQ {
   static constexpr int kKBytes = kChunks * BK * 128;      // one 64-key tile in one layout
   static constexpr int kStageBytes = 3 * kKBytes;         // K (K-major) | K (MN-major) | V (K-major)
   static constexpr int kOffQ = 0, kOffDO = kQBytes, kOffKV = 2 * kQBytes;
-  static constexpr int kOffBias = kOffKV + kStages * kStageBytes;
-  static constexpr int kOffBar = kOffBias + 2 * BK * 4;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kOffBar = kOffKV + kStages * kStageBytes;
+  static constexpr int kOffFlag = kOffBar + 256;          // [2 items][64] "all 32 keys valid" flags
+  static constexpr int kOffBias = kOffFlag + 512;         // [2 items][LkPad] additive key bias (0 / -inf), sized at launch
+  static constexpr int kSmemFixed = kOffBias + 1024;      // + 2 * LkPad * 4
   static constexpr int kColS = 0, kColDP = 128, kColDQ = 256;   // S: 2x64, dP: 2x64, dQ: DH
+  static constexpr int kColQ = 320, kColDO = 384;               // the stationary Q_i / dO_i tiles as TMEM A-operands
   static constexpr int kTmemCols = 512;
 };
 
@@ -64,18 +86,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
+  uint32_t* flags_s = reinterpret_cast<uint32_t*>(smem + C::kOffFlag);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* qdo_full = bars + 0;  uint64_t* qdo_empty = bars + 1;
   uint64_t* kv_full = bars + 2;   uint64_t* kv_empty = bars + 5;     // [3] each
   uint64_t* sdp_full = bars + 8;  uint64_t* ds_full = bars + 10;     // [2] each
   uint64_t* dq_full = bars + 12;  uint64_t* dq_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* qt_full = bars + 14;                                     // Q_i / dO_i copied into TMEM by the elementwise warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_k);
     tc::tma_prefetch_desc(&tm_k_mn); tc::tma_prefetch_desc(&tm_v);
-    tc::mbar_init(qdo_full, 1); tc::mbar_init(qdo_empty, 1);
+    tc::mbar_init(qdo_full, 1); tc::mbar_init(qdo_empty, 8); tc::mbar_init(qt_full, 8);
     for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(sdp_full + s, 1); tc::mbar_init(ds_full + s, 8); }
     tc::mbar_init(dq_full, 1); tc::mbar_init(dq_empty, 8);
@@ -96,11 +120,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
+      TRACE_DECL(true);
       uint32_t kc = 0, ic = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         coords(item, b, h, q0, n);
         tc::mbar_wait(qdo_empty, (ic & 1) ^ 1);
+        TRACE(0, 0);
         tc::mbar_arrive_expect_tx(qdo_full, 2 * C::kQBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -110,6 +136,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         for (int j = 0; j < n; ++j, ++kc) {
           const int s = kc % C::kStages;
           tc::mbar_wait(kv_empty + s, ((kc / C::kStages) & 1) ^ 1);
+          TRACE(0, 1);
           tc::mbar_arrive_expect_tx(kv_full + s, C::kStageBytes);
           uint8_t* base = smem + C::kOffKV + s * C::kStageBytes;
 #pragma unroll
@@ -120,17 +147,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
         }
       }
+      TRACE_END(0);
     }
   } else if (warp == 1) {
     // The whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues the MMAs.
     {
       constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BQ, C::BK, 0, 0);
       constexpr uint32_t idesc_dq = tc::make_idesc_tf32(C::BQ, DH, 0, 1);
+      TRACE_DECL(lane == 0);
       uint32_t kc = 0, ic = 0, st = 0, dt = 0;
-      const uint32_t sq = tc::smem_u32(smem + C::kOffQ), sdo = tc::smem_u32(smem + C::kOffDO);
+      // Q_i and dO_i are A-operands in TMEM (written once per item by the elementwise warps): in the SS form every
+      // 128x64x8 MMA re-read 4 KB of them from shared memory and the kernel ran at the shared-memory bandwidth
       auto issue_sdp = [&](uint32_t kcs) {       // S and dP of the tile held in KV stage kcs % kStages
         const int s = kcs % C::kStages;
         tc::mbar_wait(kv_full + s, (kcs / C::kStages) & 1);
+        TRACE(1, 1);
         tc::tc_fence_after();
         const uint32_t sk = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes);
         const uint32_t sv = sk + 2 * C::kKBytes;
@@ -138,37 +169,37 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (tc::elect_one()) {
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
-            const uint64_t da = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
             const uint64_t db = tc::make_smem_desc(sk + c * (C::BK * 128), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+              tc::mma_tf32_ts(tmem_base + C::kColS + buf * C::BK, tmem_base + C::kColQ + c * 32 + k * 8, tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
           }
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
-            const uint64_t da = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
             const uint64_t db = tc::make_smem_desc(sv + c * (C::BK * 128), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BK, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+              tc::mma_tf32_ts(tmem_base + C::kColDP + buf * C::BK, tmem_base + C::kColDO + c * 32 + k * 8, tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
           }
           tc::tc_commit(sdp_full + buf);
         }
         __syncwarp();
+        TRACE(1, 2);
         ++st;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
         int b, h, q0, n;
         coords(item, b, h, q0, n);
-        tc::mbar_wait(qdo_full, ic & 1);
+        tc::mbar_wait(qt_full, ic & 1);                  // Q_i / dO_i are in TMEM
         tc::mbar_wait(dq_empty, (ic & 1) ^ 1);           // previous item's dQ has been read out of TMEM
+        TRACE(1, 0);
         tc::tc_fence_after();
         issue_sdp(kc);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_sdp(kc + 1);
-          if (j + 1 == n) { if (tc::elect_one()) tc::tc_commit(qdo_empty); __syncwarp(); }      // all S/dP MMAs of this item are issued
           const int buf = dt & 1;
           tc::mbar_wait(ds_full + buf, (dt >> 1) & 1);
+          TRACE(1, 3);
           tc::tc_fence_after();
           const int s = kc % C::kStages;
           const uint32_t skm = tc::smem_u32(smem + C::kOffKV + s * C::kStageBytes + C::kKBytes);
@@ -182,9 +213,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (j + 1 == n) tc::tc_commit(dq_full);
           }
           __syncwarp();
+          TRACE(1, 4);
           ++kc; ++dt;
         }
       }
+      TRACE_END(1);
     }
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
@@ -192,6 +225,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     uint32_t sc = 0, ic = 0;
+    TRACE_DECL(lane == 0 && (warp == 2 || warp == 6));
+#ifdef PA_ATTN_TRACE
+    const int trole = warp == 2 ? 2 : 3;
+#endif
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
       int b, h, q0, n;
       coords(item, b, h, q0, n);
@@ -201,53 +238,103 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const float lse = q_ok ? p.lse[rg] : -INFINITY;
       const float lse2 = lse == -INFINITY ? INFINITY : lse * kLog2e;     // +inf => P = 0
       const float dl = q_ok ? p.delta[rg] : 0.f;
-      auto key_ok = [&](int k0n) {
-        const int kj = k0n + tid;
-        return kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+      // stationary operands: this thread's row of Q_i and dO_i (its warpgroup's 32-column chunk) from the TMA tile in
+      // shared memory (128B swizzle: 16-byte piece i of row r sits at piece i ^ (r & 7)) into TMEM.  The previous
+      // item's S/dP MMAs have all been consumed by these warps, so the TMEM columns are free.
+      tc::mbar_wait(qdo_full, ic & 1);
+      if (half < C::kChunks) {
+        const uint8_t* qrow = smem + C::kOffQ + half * (C::BQ * 128) + row * 128;
+        const uint8_t* drow = smem + C::kOffDO + half * (C::BQ * 128) + row * 128;
+        uint32_t rq[32], rdo[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int off = (i ^ (row & 7)) << 4;
+          const uint4 a4 = *reinterpret_cast<const uint4*>(qrow + off);
+          const uint4 d4 = *reinterpret_cast<const uint4*>(drow + off);
+          rq[4 * i] = a4.x; rq[4 * i + 1] = a4.y; rq[4 * i + 2] = a4.z; rq[4 * i + 3] = a4.w;
+          rdo[4 * i] = d4.x; rdo[4 * i + 1] = d4.y; rdo[4 * i + 2] = d4.z; rdo[4 * i + 3] = d4.w;
+        }
+        tc::tmem_st_32x32(tmem_base + lane_addr + C::kColQ + half * 32, rq);
+        tc::tmem_st_32x32(tmem_base + lane_addr + C::kColDO + half * 32, rdo);
+        tc::tmem_st_wait();
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(qt_full); tc::mbar_arrive(qdo_empty); }
+      // additive key bias (0 / -inf: PAD keys and keys beyond Lk) of the WHOLE item, written once; the two tables
+      // alternate between items, so one named barrier per item is all the elementwise warps need
+      float* bias_it = bias_s + (ic & 1) * p.LkPad;
+      uint32_t* flag_it = flags_s + (ic & 1) * 64;          // per 32-key group: 1 = every key valid (tiles of valid keys skip the bias)
+      for (int k = tid; k < n * C::BK; k += 256) {
+        const bool ok = k < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + k]);
+        bias_it[k] = ok ? 0.f : -INFINITY;
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) flag_it[k >> 5] = all_ok ? 1u : 0u;
+      }
+      auto load_mw = [&](int k0n) -> uint32_t {            // keep-bits of this thread's 32 keys for this query row
+        const int wi = (k0n + half * 32) >> 5;
+        return (q_ok && wi < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + wi) : 0u;
       };
-      bool ok_pref = tid < C::BK ? key_ok(0) : false;        // global loads run one tile ahead of their use
+      uint32_t mw_pref = p.p_drop > 0.f ? load_mw(0) : 0xffffffffu;     // global loads run one tile ahead of their use
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int j = 0; j < n; ++j, ++sc) {
         const int buf = sc & 1, k0 = j * C::BK;
-        if (tid < C::BK) {
-          bias_s[buf * C::BK + tid] = ok_pref ? 0.f : -INFINITY;
-          if (j + 1 < n) ok_pref = key_ok(k0 + C::BK);
-        }
-        uint32_t mw = 0xffffffffu;                           // keep-bits of this thread's 32 keys for this query row
-        if (p.p_drop > 0.f) mw = (q_ok && ((k0 + half * 32) >> 5) < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + ((k0 + half * 32) >> 5)) : 0u;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        TRACE(trole, 0);
+        const uint32_t mw = mw_pref;
+        if (p.p_drop > 0.f && j + 1 < n) mw_pref = load_mw(k0 + C::BK);
+        TRACE(trole, 1);
         tc::mbar_wait(sdp_full + buf, (sc >> 1) & 1);
+        TRACE(trole, 2);
         tc::tc_fence_after();
         const bool diag = p.causal && (k0 + C::BK - 1 > q0);
+        const bool clean = !diag && (flag_it[2 * j] & flag_it[2 * j + 1]) != 0;   // no masking needed anywhere in this tile
 #pragma unroll
         for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 32) {
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BK + c0, rd);
           tc::tmem_ld_wait();
+          TRACE(trole, 3);
+          if (clean) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float mk[4];
+            for (int c = 0; c < 32; ++c) {
+              const float mk = ((mw >> c) & 1u) ? ks : 0.f;
+              const float pr = fast_exp2(fmaf(__uint_as_float(rs[c]), p.scale_log2, -lse2));
+              const float ds = pr * fmaf(__uint_as_float(rd[c]), mk, -dl);
+              rs[c] = tf32_rn_finite_bits(ds);
+            }
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
+            for (int c = 0; c < 32; c += 4) {
+              float mk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int kk = c0 + c + e;
-              float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, bias_s[buf * C::BK + kk] - lse2);
-              if (diag && k0 + kk > qi) v = -INFINITY;
-              const float pr = fast_exp2(v);
-              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dl);
-              rs[c + e] = __float_as_uint(tf32_rn(ds));
+              for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_it + k0 + c0 + c);
+              const float bz[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int kk = c0 + c + e;
+                float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, bz[e] - lse2);
+                if (diag && k0 + kk > qi) v = -INFINITY;
+                const float pr = fast_exp2(v);
+                const float ds = pr * fmaf(__uint_as_float(rd[c + e]), mk[e], -dl);
+                rs[c + e] = tf32_rn_finite_bits(ds);
+              }
             }
           }
+          TRACE(trole, 4);
           tc::tmem_st_32x32(tmem_base + lane_addr + C::kColS + buf * C::BK + c0, rs);
         }
         tc::tmem_st_wait();
+        TRACE(trole, 5);
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(ds_full + buf);
+        TRACE(trole, 6);
       }
       // dQ_i is complete in TMEM
       tc::mbar_wait(dq_full, ic & 1);
+      TRACE(trole, 7);
       tc::tc_fence_after();
       float* out = p.dq + ((int64_t)b * p.Lq + qi) * p.lddq + h * DH;
 #pragma unroll
@@ -275,7 +362,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(dq_empty);
+      TRACE(trole, 8);
     }
+#ifdef PA_ATTN_TRACE
+    if (trace_on) g_bwd_trace_n[trole] = trace_n;
+#endif
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -573,6 +664,9 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols; p.dbias = a.dbias;
   p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
+#ifdef PA_ATTN_TRACE
+  { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & 1024) : 0; }
+#endif
   if (a.p_drop > 0.f && (a.drop_rows == nullptr || a.drop_cols == nullptr)) {
     pa_set_error("pa_attn_bwd (tc): p_drop > 0 needs drop_rows/drop_cols from pa_dropout_mask");
     return PA_ERR_ARG;
@@ -586,11 +680,14 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     if ((rc = pa_make_tmap_2d(&tkm, a.k, d, rk, (uint64_t)a.ldk * 4, 32, C::BK, true))) return rc;
     if ((rc = pa_make_tmap_2d(&tv, a.v, d, rk, (uint64_t)a.ldv * 4, 32, C::BK))) return rc;
     auto kern = attn_bwd_dq_tc_kernel<DH>;
-    static bool done = false;
-    if (!done) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem)); done = true; }
+    p.LkPad = (a.Lk + C::BK - 1) / C::BK * C::BK;
+    const int smem_q = C::kSmemFixed + 2 * p.LkPad * 4;
+    if (smem_q > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_bwd (tc): Lk = %d too long for the dQ kernel's bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
+    static int attr_q = 0;
+    if (smem_q > attr_q) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q)); attr_q = smem_q; }
     p.tiles = (a.Lq + C::BQ - 1) / C::BQ;
     p.items = p.tiles * a.H * a.B;
-    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, C::kSmem, st>>>(tq, tdo, tk, tkm, tv, p);
+    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_q, st>>>(tq, tdo, tk, tkm, tv, p);
     PA_CHECK_LAUNCH();
   }
   {
@@ -614,6 +711,14 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef PA_ATTN_TRACE
+extern "C" int pa_debug_attn_bwd_trace(unsigned long long* out_host /*[4][1024]*/, int* n_host /*[4]*/) {
+  PA_CUDA(cudaMemcpyFromSymbol(out_host, g_bwd_trace, sizeof(unsigned long long) * 4 * 1024));
+  PA_CUDA(cudaMemcpyFromSymbol(n_host, g_bwd_trace_n, sizeof(int) * 4));
+  return PA_OK;
+}
+#endif
 
 int pa_attn_bwd_tc(const pa_attn_bwd_args* a, void* stream) {
   switch (a->dh) {

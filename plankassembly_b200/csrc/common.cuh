@@ -44,6 +44,9 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+// Same rounding (nearest, ties away from zero) for values known to be finite: add half an ulp of the 10-bit mantissa
+// and clear the low 13 bits -- two integer instructions instead of cvt.rna's compare + add + mask.
+__device__ __forceinline__ uint32_t tf32_rn_finite_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
 
 // 2^x on the MUFU in one instruction (max rel. error 2^-22; -inf -> 0), for softmax probabilities
