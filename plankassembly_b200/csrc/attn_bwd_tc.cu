@@ -191,13 +191,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         int b, h, q0, n;
         coords(item, b, h, q0, n);
         tc::mbar_wait(qt_full, ic & 1);                  // Q_i / dO_i are in TMEM
-        tc::mbar_wait(dq_empty, (ic & 1) ^ 1);           // previous item's dQ has been read out of TMEM
         TRACE(1, 0);
         tc::tc_fence_after();
         issue_sdp(kc);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_sdp(kc + 1);
           const int buf = dt & 1;
+          if (j == 0) tc::mbar_wait(dq_empty, (ic & 1) ^ 1);   // previous item's dQ has been read out of TMEM
           tc::mbar_wait(ds_full + buf, (dt >> 1) & 1);
           TRACE(1, 3);
           tc::tc_fence_after();
@@ -229,19 +229,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #ifdef PA_ATTN_TRACE
     const int trole = warp == 2 ? 2 : 3;
 #endif
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-      int b, h, q0, n;
-      coords(item, b, h, q0, n);
-      const int qi = q0 + row;
-      const bool q_ok = qi < p.Lq;
-      const int64_t rg = ((int64_t)(b * p.H + h) * p.Lq + qi);
-      const float lse = q_ok ? p.lse[rg] : -INFINITY;
-      const float lse2 = lse == -INFINITY ? INFINITY : lse * kLog2e;     // +inf => P = 0
-      const float dl = q_ok ? p.delta[rg] : 0.f;
-      // stationary operands: this thread's row of Q_i and dO_i (its warpgroup's 32-column chunk) from the TMA tile in
-      // shared memory (128B swizzle: 16-byte piece i of row r sits at piece i ^ (r & 7)) into TMEM.  The previous
-      // item's S/dP MMAs have all been consumed by these warps, so the TMEM columns are free.
-      tc::mbar_wait(qdo_full, ic & 1);
+    // The items are software-pipelined: the next item's per-row scalars, key-padding bytes and first dropout word are
+    // requested, and its Q/dO rows are copied into TMEM, BEFORE the current item's dQ epilogue -- the global-load
+    // latencies and the MMA pipeline fill of item i+1 hide behind the TMEM read-out and the stores of item i.
+    constexpr int KPT = 8;                               // key-padding bytes per thread (Lk <= 2048)
+    struct ItemRegs {
+      int b, h, q0, n, qi; bool q_ok; int64_t rg;
+      float lse, dl; uint8_t kp[KPT]; uint32_t mw0;
+    };
+    auto prefetch = [&](int item, ItemRegs& r) {         // only ISSUES the loads
+      coords(item, r.b, r.h, r.q0, r.n);
+      r.qi = r.q0 + row;
+      r.q_ok = r.qi < p.Lq;
+      r.rg = ((int64_t)(r.b * p.H + r.h) * p.Lq + r.qi);
+      r.lse = r.q_ok ? p.lse[r.rg] : -INFINITY;
+      r.dl = r.q_ok ? p.delta[r.rg] : 0.f;
+#pragma unroll
+      for (int m = 0; m < KPT; ++m) {
+        const int k = tid + 256 * m;
+        r.kp[m] = (p.kpm != nullptr && k < p.Lk && k < r.n * C::BK) ? p.kpm[(int64_t)r.b * p.Lk + k] : (uint8_t)0;
+      }
+      const int wi = (half * 32) >> 5;
+      r.mw0 = p.p_drop > 0.f ? ((r.q_ok && wi < p.LkW) ? __ldg(p.drop_rows + r.rg * p.LkW + wi) : 0u) : 0xffffffffu;
+    };
+    // stationary operands: this thread's row of Q_i and dO_i (its warpgroup's 32-column chunk) from the TMA tile in
+    // shared memory (128B swizzle: 16-byte piece i of row r sits at piece i ^ (r & 7)) into TMEM.  Called when every
+    // S/dP MMA of the previous item has been consumed by these warps, so the TMEM columns are free.
+    auto copy_qdo = [&](uint32_t icn) {
+      TRACE(trole, 9);
+      tc::mbar_wait(qdo_full, icn & 1);
+      TRACE(trole, 10);
       if (half < C::kChunks) {
         const uint8_t* qrow = smem + C::kOffQ + half * (C::BQ * 128) + row * 128;
         const uint8_t* drow = smem + C::kOffDO + half * (C::BQ * 128) + row * 128;
@@ -261,22 +278,40 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(qt_full); tc::mbar_arrive(qdo_empty); }
+      TRACE(trole, 11);
+    };
+
+    ItemRegs nx;
+    if ((int)blockIdx.x < p.items) { prefetch(blockIdx.x, nx); copy_qdo(0); }
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+      const ItemRegs cu = nx;
+      const int b = cu.b, h = cu.h, q0 = cu.q0, n = cu.n, qi = cu.qi;
+      const bool q_ok = cu.q_ok;
+      const int64_t rg = cu.rg;
+      const float lse2 = cu.lse == -INFINITY ? INFINITY : cu.lse * kLog2e;     // +inf => P = 0
+      const float dl = cu.dl;
       // additive key bias (0 / -inf: PAD keys and keys beyond Lk) of the WHOLE item, written once; the two tables
       // alternate between items, so one named barrier per item is all the elementwise warps need
       float* bias_it = bias_s + (ic & 1) * p.LkPad;
       uint32_t* flag_it = flags_s + (ic & 1) * 64;          // per 32-key group: 1 = every key valid (tiles of valid keys skip the bias)
-      for (int k = tid; k < n * C::BK; k += 256) {
-        const bool ok = k < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + k]);
-        bias_it[k] = ok ? 0.f : -INFINITY;
-        const bool all_ok = __all_sync(0xffffffffu, ok);
-        if (lane == 0) flag_it[k >> 5] = all_ok ? 1u : 0u;
+#pragma unroll
+      for (int m = 0; m < KPT; ++m) {
+        const int k = tid + 256 * m;
+        if (k < n * C::BK) {
+          const bool ok = k < p.Lk && !cu.kp[m];
+          bias_it[k] = ok ? 0.f : -INFINITY;
+          const bool all_ok = __all_sync(0xffffffffu, ok);
+          if (lane == 0) flag_it[k >> 5] = all_ok ? 1u : 0u;
+        }
       }
       auto load_mw = [&](int k0n) -> uint32_t {            // keep-bits of this thread's 32 keys for this query row
         const int wi = (k0n + half * 32) >> 5;
         return (q_ok && wi < p.LkW) ? __ldg(p.drop_rows + rg * p.LkW + wi) : 0u;
       };
-      uint32_t mw_pref = p.p_drop > 0.f ? load_mw(0) : 0xffffffffu;     // global loads run one tile ahead of their use
+      uint32_t mw_pref = cu.mw0;                           // global loads run one tile ahead of their use
+      TRACE(trole, 12);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      TRACE(trole, 13);
       for (int j = 0; j < n; ++j, ++sc) {
         const int buf = sc & 1, k0 = j * C::BK;
         TRACE(trole, 0);
@@ -332,6 +367,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (lane == 0) tc::mbar_arrive(ds_full + buf);
         TRACE(trole, 6);
       }
+      // item boundary: get the next item going before this item's read-out
+      const int next_item = item + gridDim.x;
+      if (next_item < p.items) { prefetch(next_item, nx); copy_qdo(ic + 1); }
       // dQ_i is complete in TMEM
       tc::mbar_wait(dq_full, ic & 1);
       TRACE(trole, 7);
