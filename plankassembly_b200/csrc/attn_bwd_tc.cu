@@ -33,7 +33,7 @@ __device__ int g_bwd_trace_n[4];
   do {                                                                                           \
     if (trace_on && trace_n < 1024) g_bwd_trace[role][trace_n++] = ((unsigned long long)(ev) << 56) | (clock64() & 0xffffffffffffffull); \
   } while (0)
-#define TRACE_DECL(cond) const bool trace_on = p.trace && blockIdx.x == 0 && (cond); int trace_n = 0
+#define TRACE_DECL(cond) const bool trace_on = (p.trace & kTraceBit) && blockIdx.x == 0 && (cond); int trace_n = 0
 #define TRACE_END(role) do { if (trace_on) g_bwd_trace_n[role] = trace_n; } while (0)
 #else
 #define TRACE(role, ev) do {} while (0)
@@ -55,6 +55,7 @@ struct BwdParams {
   float* dbias;          // [3*H*DH] += column sums of dq | dk | dv (in-projection bias gradient), may be NULL
   int tiles, items;
   int LkPad;             // keys rounded up to the key tile (per-item bias table length)
+  int LqPad;             // queries rounded up to the query tile (per-item lse/delta table length)
   int trace;
 };
 
@@ -83,6 +84,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_k_mn,
                       const __grid_constant__ CUtensorMap tm_v, const BwdParams p) {
   using C = CfgQ<DH>;
+  constexpr int kTraceBit = 1024; (void)kTraceBit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
@@ -421,9 +423,9 @@ template <int DH> struct CfgK {
   static constexpr int kQBytes = kChunks * BQ * 128;      // one 64-query tile in one layout
   static constexpr int kStageBytes = 4 * kQBytes;         // Q K-major | Q MN-major | dO K-major | dO MN-major
   static constexpr int kOffK = 0, kOffV = kKVBytes, kOffQ = 2 * kKVBytes;
-  static constexpr int kOffStat = kOffQ + kStages * kStageBytes;      // [2 bufs][lse2 | delta][64]
-  static constexpr int kOffBar = kOffStat + 2 * 2 * BQ * 4;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kOffBar = kOffQ + kStages * kStageBytes;
+  static constexpr int kOffStat = kOffBar + 256;                      // [2 items][lse2 | delta][LqPad], sized at launch
+  static constexpr int kSmemFixed = kOffStat + 1024;                  // + 2 * 2 * LqPad * 4
   static constexpr int kColS = 0, kColDP = 128, kColDK = 256, kColDV = 256 + DH;
   static constexpr int kTmemCols = 512;
 };
@@ -435,22 +437,30 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
                         const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_do_mn,
                         const BwdParams p) {
   using C = CfgK<DH>;
+  constexpr int kTraceBit = 2048; (void)kTraceBit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* stat_s = reinterpret_cast<float*>(smem + C::kOffStat);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* kv_full = bars + 0;   uint64_t* kv_empty = bars + 1;
-  uint64_t* q_full = bars + 2;    uint64_t* q_empty = bars + 4;      // [2] each
+  // Each query-tile stage is two half-stages with their own barriers: the K-major copies of Q_i / dO_i are released as
+  // soon as S^T / dP^T have been computed (one tile earlier than the MN-major copies, which dV / dK read) -- with a
+  // single release per stage the TMA refill of a slot started exactly when its data was needed next.
+  uint64_t* q_full = bars + 2;    uint64_t* q_empty = bars + 4;      // [2] each: K-major halves
+  uint64_t* qm_full = bars + 12;  uint64_t* qm_empty = bars + 14;    // [2] each: MN-major halves
   uint64_t* st_full = bars + 6;   uint64_t* pds_full = bars + 8;     // [2] each
   uint64_t* acc_full = bars + 10; uint64_t* acc_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v); tc::tma_prefetch_desc(&tm_q);
     tc::tma_prefetch_desc(&tm_q_mn); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_do_mn);
     tc::mbar_init(kv_full, 1); tc::mbar_init(kv_empty, 1);
-    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(q_full + s, 1); tc::mbar_init(q_empty + s, 1); }
+    for (int s = 0; s < C::kStages; ++s) {
+      tc::mbar_init(q_full + s, 1); tc::mbar_init(q_empty + s, 1);
+      tc::mbar_init(qm_full + s, 1); tc::mbar_init(qm_empty + s, 1);
+    }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(st_full + s, 1); tc::mbar_init(pds_full + s, 8); }
     tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 8);
     tc::fence_barrier_init();
@@ -483,17 +493,23 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         }
         for (int i = i0; i < q_tiles_all; ++i, ++qc) {
           const int s = qc % C::kStages;
-          tc::mbar_wait(q_empty + s, ((qc / C::kStages) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(q_full + s, C::kStageBytes);
           uint8_t* base = smem + C::kOffQ + s * C::kStageBytes;
           const int y = b * p.Lq + i * C::BQ;
+          tc::mbar_wait(q_empty + s, ((qc / C::kStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(q_full + s, 2 * C::kQBytes);
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
             const int x = h * DH + c * 32, off = c * (C::BQ * 128);
             tc::tma_load_2d(base + off, &tm_q, x, y, q_full + s);
-            tc::tma_load_2d(base + C::kQBytes + off, &tm_q_mn, x, y, q_full + s);
             tc::tma_load_2d(base + 2 * C::kQBytes + off, &tm_do, x, y, q_full + s);
-            tc::tma_load_2d(base + 3 * C::kQBytes + off, &tm_do_mn, x, y, q_full + s);
+          }
+          tc::mbar_wait(qm_empty + s, ((qc / C::kStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(qm_full + s, 2 * C::kQBytes);
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            const int x = h * DH + c * 32, off = c * (C::BQ * 128);
+            tc::tma_load_2d(base + C::kQBytes + off, &tm_q_mn, x, y, qm_full + s);
+            tc::tma_load_2d(base + 3 * C::kQBytes + off, &tm_do_mn, x, y, qm_full + s);
           }
         }
       }
@@ -503,11 +519,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     {
       constexpr uint32_t idesc_s = tc::make_idesc_tf32(C::BKV, C::BQ, 0, 0);      // [128 keys x 64 queries]
       constexpr uint32_t idesc_acc = tc::make_idesc_tf32(C::BKV, DH, 0, 1);       // [128 keys x DH]
+      TRACE_DECL(lane == 0);
       uint32_t qc = 0, ic = 0, st = 0, dt = 0;
       const uint32_t sk = tc::smem_u32(smem + C::kOffK), sv = tc::smem_u32(smem + C::kOffV);
       auto issue_st = [&](uint32_t qcs) {
         const int s = qcs % C::kStages;
         tc::mbar_wait(q_full + s, (qcs / C::kStages) & 1);
+        TRACE(1, 1);
         tc::tc_fence_after();
         const uint32_t sq = tc::smem_u32(smem + C::kOffQ + s * C::kStageBytes);
         const uint32_t sdo = sq + 2 * C::kQBytes;
@@ -529,9 +547,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             for (int k = 0; k < 4; ++k)
               tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
           }
+          tc::tc_commit(q_empty + s);                    // the K-major halves are free once these retire
           tc::tc_commit(st_full + buf);
         }
         __syncwarp();
+        TRACE(1, 2);
         ++st;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
@@ -539,16 +559,20 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         coords(item, b, h, k0, i0);
         const int n = q_tiles_all - i0;
         tc::mbar_wait(kv_full, ic & 1);
-        tc::mbar_wait(acc_empty, (ic & 1) ^ 1);
         tc::tc_fence_after();
         if (n > 0) issue_st(qc);
+        else tc::mbar_wait(acc_empty, (ic & 1) ^ 1);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_st(qc + 1);
           if (j + 1 == n) { if (tc::elect_one()) tc::tc_commit(kv_empty); __syncwarp(); }       // K_j / V_j no longer needed once these retire
           const int buf = dt & 1;
+          if (j == 0) tc::mbar_wait(acc_empty, (ic & 1) ^ 1);    // previous item's dK/dV have been read out of TMEM
           tc::mbar_wait(pds_full + buf, (dt >> 1) & 1);
+          TRACE(1, 3);
           tc::tc_fence_after();
           const int s = qc % C::kStages;
+          tc::mbar_wait(qm_full + s, (qc / C::kStages) & 1);
+          tc::tc_fence_after();
           const uint32_t sqm = tc::smem_u32(smem + C::kOffQ + s * C::kStageBytes + C::kQBytes);
           const uint32_t sdom = sqm + 2 * C::kQBytes;
           const uint64_t dqm = tc::make_smem_desc(sqm, C::BQ * 128, 512, tc::kLayoutSw128Base32);
@@ -562,9 +586,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             for (int k = 0; k < C::BQ / 8; ++k)      // dK += dS^T Q_i
               tc::mma_tf32_ts(tmem_base + C::kColDK, tmem_base + C::kColDP + buf * C::BQ + k * 8, tc::desc_advance(dqm, k * 1024), idesc_acc,
                               (j > 0 || k > 0) ? 1u : 0u);
-            tc::tc_commit(q_empty + s);
+            tc::tc_commit(qm_empty + s);
           }
           __syncwarp();
+          TRACE(1, 4);
           ++qc; ++dt;
         }
         if (tc::elect_one()) {
@@ -573,6 +598,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         }
         __syncwarp();
       }
+      TRACE_END(1);
     }
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane, tid = threadIdx.x - 64;
@@ -580,44 +606,71 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     uint32_t sc = 0, ic = 0;
+    // Items are software-pipelined like in the dQ kernel: the next item's key-padding byte, the lse/delta of ALL its
+    // queries and its first dropout word are requested before the current item's dK/dV read-out; the stats go into a
+    // per-item smem table (two tables alternate), so the tile loop has no named barrier and no global-load latency.
+    TRACE_DECL(lane == 0 && (warp == 2 || warp == 6));
+#ifdef PA_ATTN_TRACE
+    const int trole = warp == 2 ? 2 : 3;
+#endif
+    constexpr int SPT = 10;                              // table values per thread: 2 * LqPad <= 2560
+    struct ItemRegs {
+      int b, h, k0, i0, kj; uint8_t kp; float st[SPT]; uint32_t mw0;
+    };
+    auto load_mw_at = [&](int b_, int h_, int kj_, int q0n) -> uint32_t {   // keep-bits of 32 queries for this key (column plane)
+      const int wi = (q0n + half * 32) >> 5;
+      return (kj_ < p.LkW * 32 && wi < p.LqW)
+                 ? __ldg(p.drop_cols + ((int64_t)(b_ * p.H + h_) * (p.LkW * 32) + kj_) * p.LqW + wi) : 0u;
+    };
+    auto prefetch = [&](int item, ItemRegs& r) {         // only ISSUES the loads
+      coords(item, r.b, r.h, r.k0, r.i0);
+      r.kj = r.k0 + row;
+      r.kp = (p.kpm != nullptr && r.kj < p.Lk) ? p.kpm[(int64_t)r.b * p.Lk + r.kj] : (uint8_t)0;
+      const int64_t rows = (int64_t)(r.b * p.H + r.h) * p.Lq;
+#pragma unroll
+      for (int m = 0; m < SPT; ++m) {
+        const int v = tid + 256 * m;
+        float x = 0.f;
+        if (v < p.LqPad) x = v < p.Lq ? p.lse[rows + v] : -INFINITY;
+        else if (v < 2 * p.LqPad) x = (v - p.LqPad) < p.Lq ? p.delta[rows + v - p.LqPad] : 0.f;
+        r.st[m] = x;
+      }
+      r.mw0 = p.p_drop > 0.f ? load_mw_at(r.b, r.h, r.kj, r.i0 * C::BQ) : 0xffffffffu;
+    };
+    ItemRegs nx;
+    if ((int)blockIdx.x < p.items) prefetch(blockIdx.x, nx);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-      int b, h, k0, i0;
-      coords(item, b, h, k0, i0);
-      const int kj = k0 + row;
-      const bool k_ok = kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
-      const int64_t bh_rows = (int64_t)(b * p.H + h) * p.Lq;
+      const ItemRegs cu = nx;
+      const int b = cu.b, h = cu.h, k0 = cu.k0, i0 = cu.i0, kj = cu.kj;
+      const bool k_ok = kj < p.Lk && !cu.kp;
       const int n = q_tiles_all - i0;
-      auto load_stat = [&](int q0n) -> float {   // lse (log2 domain; +inf kills the row) for tid < 64, delta for 64..127
-        const int q = q0n + (tid & 63);
-        if (tid < 64) {
-          const float l = q < p.Lq ? p.lse[bh_rows + q] : -INFINITY;
-          return l == -INFINITY ? INFINITY : l * kLog2e;
-        }
-        return q < p.Lq ? p.delta[bh_rows + q] : 0.f;
-      };
-      float stat_pref = (tid < 128 && n > 0) ? load_stat(i0 * C::BQ) : 0.f;   // global loads run one tile ahead
+      float* stat_it = stat_s + (ic & 1) * 2 * p.LqPad;   // [lse in the log2 domain (+inf kills the row) | delta]
+#pragma unroll
+      for (int m = 0; m < SPT; ++m) {
+        const int v = tid + 256 * m;
+        if (v < p.LqPad) stat_it[v] = cu.st[m] == -INFINITY ? INFINITY : cu.st[m] * kLog2e;
+        else if (v < 2 * p.LqPad) stat_it[v] = cu.st[m];
+      }
+      uint32_t mw_pref = cu.mw0;                           // global loads run one tile ahead of their use
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int j = 0; j < n; ++j, ++sc) {
         const int buf = sc & 1, q0 = (i0 + j) * C::BQ;
-        if (tid < 128) {
-          stat_s[buf * 128 + tid] = stat_pref;
-          if (j + 1 < n) stat_pref = load_stat(q0 + C::BQ);
-        }
-        uint32_t mw = 0xffffffffu;              // keep-bits of this thread's 32 queries for this key (column plane)
-        if (p.p_drop > 0.f)
-          mw = (kj < p.LkW * 32 && ((q0 + half * 32) >> 5) < p.LqW)
-                   ? __ldg(p.drop_cols + ((int64_t)(b * p.H + h) * (p.LkW * 32) + kj) * p.LqW + ((q0 + half * 32) >> 5)) : 0u;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t mw = mw_pref;
+        TRACE(trole, 0);
+        if (p.p_drop > 0.f && j + 1 < n) mw_pref = load_mw_at(b, h, kj, q0 + C::BQ);
         tc::mbar_wait(st_full + buf, (sc >> 1) & 1);
+        TRACE(trole, 2);
         tc::tc_fence_after();
         const bool diag = p.causal && (q0 < k0 + C::BKV - 1);
-        const float* lse2 = stat_s + buf * 128;
-        const float* dl = lse2 + 64;
+        const float* lse2 = stat_it + q0;
+        const float* dl = stat_it + p.LqPad + q0;
 #pragma unroll
         for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 32) {
           uint32_t rs[32], rd[32];
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
           tc::tmem_ld_wait();
+          TRACE(trole, 3);
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             float mk[4];
@@ -638,15 +691,20 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
               rd[c + e] = __float_as_uint(tf32_rn(ds));
             }
           }
+          TRACE(trole, 4);
           tc::tmem_st_32x32(tmem_base + lane_addr + C::kColS + buf * C::BQ + c0, rs);
           tc::tmem_st_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
         }
         tc::tmem_st_wait();
+        TRACE(trole, 5);
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(pds_full + buf);
+        TRACE(trole, 6);
       }
+      if (item + (int)gridDim.x < p.items) prefetch(item + gridDim.x, nx);    // next item's loads fly during the read-out
       tc::mbar_wait(acc_full, ic & 1);
+      TRACE(trole, 7);
       tc::tc_fence_after();
       const bool row_ok = kj < p.Lk;
       float* outk = p.dk + ((int64_t)b * p.Lk + kj) * p.lddk + h * DH;
@@ -683,7 +741,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc_empty);
+      TRACE(trole, 8);
     }
+#ifdef PA_ATTN_TRACE
+    if (trace_on) g_bwd_trace_n[trole] = trace_n;
+#endif
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -703,7 +765,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols; p.dbias = a.dbias;
   p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
 #ifdef PA_ATTN_TRACE
-  { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & 1024) : 0; }
+  { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & (1024 | 2048)) : 0; }
 #endif
   if (a.p_drop > 0.f && (a.drop_rows == nullptr || a.drop_cols == nullptr)) {
     pa_set_error("pa_attn_bwd (tc): p_drop > 0 needs drop_rows/drop_cols from pa_dropout_mask");
@@ -738,11 +800,14 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     if ((rc = pa_make_tmap_2d(&tdo, a.d_o, d, rq, (uint64_t)a.ldo * 4, 32, C::BQ))) return rc;
     if ((rc = pa_make_tmap_2d(&tdom, a.d_o, d, rq, (uint64_t)a.ldo * 4, 32, C::BQ, true))) return rc;
     auto kern = attn_bwd_dkdv_tc_kernel<DH>;
-    static bool done = false;
-    if (!done) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem)); done = true; }
+    p.LqPad = (a.Lq + C::BQ - 1) / C::BQ * C::BQ;
+    const int smem_k = C::kSmemFixed + 2 * 2 * p.LqPad * 4;
+    if (smem_k > 227 * 1024 || 2 * p.LqPad > 2560) { pa_set_error("pa_attn_bwd (tc): Lq = %d too long for the dK/dV kernel's stat table", a.Lq); return PA_ERR_UNSUPPORTED; }
+    static int attr_k = 0;
+    if (smem_k > attr_k) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_k)); attr_k = smem_k; }
     p.tiles = (a.Lk + C::BKV - 1) / C::BKV;
     p.items = p.tiles * a.H * a.B;
-    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, C::kSmem, st>>>(tk, tv, tq, tqm, tdo, tdom, p);
+    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_k, st>>>(tk, tv, tq, tqm, tdo, tdom, p);
     PA_CHECK_LAUNCH();
   }
   return PA_OK;

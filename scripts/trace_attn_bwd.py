@@ -1,7 +1,7 @@
 """Event timeline of CTA 0 of the tensor-core attention dQ kernel (library built with PLANK_B200_NVCC_FLAGS=-DPA_ATTN_TRACE)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ['PLANK_B200_ATTN_DEBUG'] = '1024'
+os.environ['PLANK_B200_ATTN_DEBUG'] = os.environ.get('TRACE_KERNEL', '1024')   # 1024 = dQ kernel, 2048 = dK/dV kernel
 import torch
 from plankassembly_b200 import ops, _lib
 B, H, dh, L = 64, 8, 64, 512
