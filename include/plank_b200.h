@@ -85,8 +85,8 @@ int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
  * impl: 0 = fp32 SIMT (exact mode), 1 = tcgen05 TF32 tensor-core path. */
 /* Attention-probability dropout keep-masks for the tensor-core kernels, generated ONCE per attention call
  * (all warps of the chip) instead of three times inside the forward / dQ / dK-dV kernels (4 warps per SM):
- * bit = Philox4x32-10(seed, counter = (bh*Lq + q)*ceil(Lk/4) + k/4, offset)[k%4] >= p*2^32, i.e. exactly the
- * mask the fp32 kernels derive inline.  rows: [BH, Lq, ceil(Lk/32)] words, bit k%32 of word k/32;
+ * 16 random bits per score: bit = half-word k%2 of word (k%8)/2 of Philox4x32-10(seed, counter = (bh*Lq + q)*ceil(Lk/8)
+ * + k/8, offset) >= p*2^16, i.e. exactly the mask the fp32 kernels derive inline.  rows: [BH, Lq, ceil(Lk/32)] words, bit k%32 of word k/32;
  * cols: [BH, 32*ceil(Lk/32), ceil(Lq/32)] words, bit q%32 of word q/32 (the key-stationary backward's view). */
 size_t pa_dropout_mask_words(int BH, int Lq, int Lk, int cols);
 int pa_dropout_mask(uint32_t* rows, uint32_t* cols, int BH, int Lq, int Lk, float p_drop, uint64_t seed,

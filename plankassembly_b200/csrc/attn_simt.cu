@@ -109,11 +109,13 @@ struct DropCtx {
   bool on;
 };
 
-// keep-mask for the 4 consecutive keys kj0..kj0+3 of query row `row_global` (= (b*H+h)*Lq + qi)
-__device__ __forceinline__ void drop_mask4(const DropCtx& D, int64_t row_global, int Lk4, int kj0, float m[4]) {
-  uint4 r = philox4x32(D.seed, (uint64_t)(row_global * Lk4 + (kj0 >> 2)), D.offset);
-  m[0] = r.x >= D.thr ? D.ks : 0.f; m[1] = r.y >= D.thr ? D.ks : 0.f;
-  m[2] = r.z >= D.thr ? D.ks : 0.f; m[3] = r.w >= D.thr ? D.ks : 0.f;
+// keep-mask for the 4 consecutive keys kj0..kj0+3 (kj0 % 4 == 0) of query row `row_global` (= (b*H+h)*Lq + qi):
+// Philox counter = row_global * ceil(Lk/8) + k/8; key k uses 16 bits: word (k%8)/2, half k%2 (same rule as dropmask.cu)
+__device__ __forceinline__ void drop_mask4(const DropCtx& D, int64_t row_global, int Lk8, int kj0, float m[4]) {
+  const uint4 r = philox4x32(D.seed, (uint64_t)(row_global * Lk8 + (kj0 >> 3)), D.offset);
+  const uint32_t w0 = (kj0 & 4) ? r.z : r.x, w1 = (kj0 & 4) ? r.w : r.y;
+  m[0] = (w0 & 0xffffu) >= D.thr ? D.ks : 0.f; m[1] = (w0 >> 16) >= D.thr ? D.ks : 0.f;
+  m[2] = (w1 & 0xffffu) >= D.thr ? D.ks : 0.f; m[3] = (w1 >> 16) >= D.thr ? D.ks : 0.f;
 }
 
 template <int DH>
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__(NT) attn_fwd_simt_kernel(pa_attn_fwd_args A) {
   const float* qp = A.q + (int64_t)b * A.Lq * A.ldq + h * DH;
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
-  DropCtx D{A.seed, A.offset, drop_threshold(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 3) / 4;
+  DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
+  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
 
   load_tile<DH, false>(Qs, qp, A.ldq, q0, A.Lq);
   float m_run[4], l_run[4], o[4][W];
@@ -270,8 +272,8 @@ __global__ void __launch_bounds__(NT) attn_bwd_dkdv_simt_kernel(pa_attn_bwd_args
   const float* dop = A.d_o + (int64_t)b * A.Lq * A.ldo + h * DH;
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
-  DropCtx D{A.seed, A.offset, drop_threshold(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 3) / 4;
+  DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
+  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
   load_tile<DH, true>(Ks, kp, A.ldk, k0, A.Lk);
   load_tile<DH, true>(Vs, vp, A.ldv, k0, A.Lk);
   if (threadIdx.x < BN) {
@@ -328,8 +330,8 @@ __global__ void __launch_bounds__(NT) attn_bwd_dq_simt_kernel(pa_attn_bwd_args A
   const float* dop = A.d_o + (int64_t)b * A.Lq * A.ldo + h * DH;
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
-  DropCtx D{A.seed, A.offset, drop_threshold(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 3) / 4;
+  DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
+  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
   load_tile<DH, false>(Qs, qp, A.ldq, q0, A.Lq);
   load_tile<DH, false>(dOs, dop, A.ldo, q0, A.Lq);
   if (threadIdx.x < BM) {

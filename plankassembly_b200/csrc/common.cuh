@@ -100,6 +100,13 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Attention-probability dropout draws 16 random bits per score (one Philox4x32-10 call covers 8 consecutive keys):
+// keep iff half-word >= p * 2^16, i.e. the drop probability is p rounded down to a multiple of 2^-16.
+__host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
+  double t = (double)p * 65536.0;
+  return t >= 65535.0 ? 0xFFFFu : (uint32_t)t;
+}
+
 // keep-decision for one element: u32 random >= threshold  (threshold = p * 2^32)
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;

@@ -1,7 +1,7 @@
 // Attention-probability dropout masks as bit planes, generated once per attention call by the whole chip.
 // Inside the tensor-core attention kernels only 4 warps per SM do elementwise work, and Philox4x32-10 was
 // ~2/3 of their instructions (and was recomputed in the forward, dQ and dK/dV kernels).  Here every thread
-// owns (query q, 32 consecutive keys): 8 Philox words -> one row-major mask word; 32 ballots transpose the
+// owns (query q, 32 consecutive keys): 4 Philox calls (16 random bits per key) -> one row-major mask word; 32 ballots transpose the
 // 32x32 block so that the key-stationary backward can read its (key, 32 queries) word directly.
 #include "common.cuh"
 
@@ -15,17 +15,19 @@ __global__ void __launch_bounds__(128) dropout_mask_kernel(uint32_t* __restrict_
   const int bh = blockIdx.z;
   if (kw >= LkW) return;
   const int q = qb * 32 + lane;
-  const int Lk4 = (Lk + 3) / 4;
+  const int Lk8 = (Lk + 7) / 8;
   uint32_t word = 0;
   if (q < Lq) {
     const int64_t rg = (int64_t)bh * Lq + q;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int k4 = kw * 8 + g;
-      if (k4 < Lk4) {
-        uint4 r = philox4x32(seed, (uint64_t)(rg * Lk4 + k4), offset);
-        word |= (uint32_t)(r.x >= thr) << (4 * g) | (uint32_t)(r.y >= thr) << (4 * g + 1) |
-                (uint32_t)(r.z >= thr) << (4 * g + 2) | (uint32_t)(r.w >= thr) << (4 * g + 3);
+    for (int g = 0; g < 4; ++g) {
+      const int k8 = kw * 4 + g;
+      if (k8 < Lk8) {
+        const uint4 r = philox4x32(seed, (uint64_t)(rg * Lk8 + k8), offset);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          word |= (uint32_t)((w[e] & 0xffffu) >= thr) << (8 * g + 2 * e) | (uint32_t)((w[e] >> 16) >= thr) << (8 * g + 2 * e + 1);
       }
     }
     rows[rg * LkW + kw] = word;
@@ -53,7 +55,7 @@ extern "C" int pa_dropout_mask(uint32_t* rows, uint32_t* cols, int BH, int Lq, i
   PA_CHECK_ARG(rows != nullptr && BH > 0 && Lq > 0 && Lk > 0 && p_drop > 0.f && p_drop < 1.f);
   const int LkW = (Lk + 31) / 32, LqW = (Lq + 31) / 32;
   dim3 grid((LkW + 3) / 4, LqW, BH);
-  dropout_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rows, cols, Lq, Lk, LkW, LqW, drop_threshold(p_drop), seed, offset);
+  dropout_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rows, cols, Lq, Lk, LkW, LqW, drop_threshold16(p_drop), seed, offset);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
