@@ -207,6 +207,8 @@ class PlankModel(nn.Module):
         output_value, output_label = batch['output_value'], batch['output_label']
         T = output_value.shape[1]
         tf = self._tf32()
+        if torch.is_grad_enabled():
+            ops.zero_pool.begin_step(output_value.device)      # one memset for all zero-initialised gradient buffers
 
         if tf:
             x, x_r = self._embed_input(inputs, True)

@@ -21,6 +21,40 @@ ATTN_IMPL = {'simt': 0, 'tc': 1}
 BWD_TC = os.environ.get('PLANK_B200_ATTN_BWD', 'tc') == 'tc'   # tensor-core backward when the forward was tensor-core
 
 
+class _ZeroPool:
+    """Zero-initialised gradient buffers of one backward pass carved out of ONE pre-zeroed allocation (one memset launch per
+    step instead of ~200 small fill kernels).  The demand of a step is learned from the previous one; anything beyond it
+    falls back to torch.zeros.  The returned tensors are ordinary views: they keep the block alive for as long as they live."""
+
+    def __init__(self):
+        self.buf, self.off, self.demand, self.high = None, 0, 0, 0
+
+    def begin_step(self, device):
+        self.high = max(self.high, self.demand)
+        self.demand, self.off = 0, 0
+        self.buf = torch.zeros(self.high, device=device, dtype=torch.float32) if self.high else None
+
+    def zeros(self, shape, device):
+        n = 1
+        for x in shape:
+            n *= int(x)
+        n_al = (n + 63) // 64 * 64                      # 256-byte granules: TMA and float4 alignment
+        self.demand += n_al
+        b = self.buf
+        if b is None or b.device != device or self.off + n_al > b.numel():
+            return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+        out = b[self.off:self.off + n].view(tuple(shape))
+        self.off += n_al
+        return out
+
+
+zero_pool = _ZeroPool()
+
+
+def _zeros(shape, device):
+    return zero_pool.zeros(shape, device)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -81,7 +115,7 @@ class EmbedInput(Function):
     @once_differentiable
     def backward(ctx, dout, dout_r=None):
         dout = dout.contiguous() if dout_r is None else dout + dout_r
-        grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes]
+        grads = [_zeros(s, dout.device) for s in ctx.shapes]
         rows = (C.c_int * ctx.n)(*[s[0] for s in ctx.shapes])
         B, S = ctx.ids[0].shape
         call('pa_embed_input_bwd', dout.data_ptr(), _ptr_array([i.data_ptr() for i in ctx.ids]),
@@ -109,7 +143,7 @@ class EmbedOutput(Function):
     @once_differentiable
     def backward(ctx, dout, dout_r=None):
         dout = dout.contiguous() if dout_r is None else dout + dout_r
-        gv, gc, gp = (torch.zeros(s, device=dout.device, dtype=torch.float32) for s in ctx.shapes)
+        gv, gc, gp = (_zeros(s, dout.device) for s in ctx.shapes)
         call('pa_embed_output_bwd', dout.data_ptr(), ctx.value.data_ptr(), ctx.value.stride(0), dout.shape[0], ctx.T,
              ctx.dof, gv.data_ptr(), gc.data_ptr(), gp.data_ptr(), dout.shape[-1], _stream())
         return None, None, None, None, gv, gc, gp
@@ -151,9 +185,9 @@ class AddLayerNorm(Function):
         rows = s.numel() // d
         dx = torch.empty_like(s)
         da = torch.empty_like(s) if (ctx.has_a and (ctx.p > 0 or ctx.round_da or ctx.has_bias)) else None
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
-        dabias = torch.zeros_like(gamma) if ctx.has_bias else None
+        dgamma = _zeros(gamma.shape, gamma.device)
+        dbeta = _zeros(gamma.shape, gamma.device)
+        dabias = _zeros(gamma.shape, gamma.device) if ctx.has_bias else None
         ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=s.device, dtype=torch.uint8)
         call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed,
              ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
@@ -245,7 +279,7 @@ class SelfAttention(Function):
         d = d3 // 3
         dqkv = torch.empty_like(qkv)
         bimpl = impl if BWD_TC else 0
-        dbias = torch.zeros(d3, device=qkv.device, dtype=torch.float32) if (has_bias and bimpl == 1) else None
+        dbias = _zeros((d3,), qkv.device) if (has_bias and bimpl == 1) else None
         base, g = qkv.data_ptr(), dqkv.data_ptr()
         _attn_bwd(base, base + 4 * d, base + 8 * d, d3, d3, d3, o, do.contiguous(), lse, g, g + 4 * d, g + 8 * d, d3, d3, d3,
                   B, H, L, L, d // H, kpm, causal, p_drop, seed, off, bimpl, rnd, (m_rows, m_cols), dbias)
@@ -281,7 +315,7 @@ class CrossAttention(Function):
         Lk = kv.shape[1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         bimpl = impl if BWD_TC else 0
-        dbias = torch.zeros(3 * d, device=q.device, dtype=torch.float32) if (has_bias and bimpl == 1) else None
+        dbias = _zeros((3 * d,), q.device) if (has_bias and bimpl == 1) else None
         kb, gb = kv.data_ptr(), dkv.data_ptr()
         _attn_bwd(q.data_ptr(), kb, kb + 4 * d, d, 2 * d, 2 * d, o, do.contiguous(), lse, dq.data_ptr(), gb, gb + 4 * d,
                   d, 2 * d, 2 * d, B, H, Lq, Lk, d // H, kpm, False, p_drop, seed, off, bimpl, rnd, (m_rows, m_cols), dbias)
@@ -360,7 +394,7 @@ class Linear(Function):
         if y is not None:
             dy2 = dy2.clone()
             if want_db and N % 4 == 0 and N // 4 <= 256 and 256 % (N // 4) == 0:
-                db = torch.zeros(N, device=dy.device, dtype=torch.float32)     # bias grad = column sums, fused
+                db = _zeros((N,), dy.device)     # bias grad = column sums, fused
                 call('pa_relu_dropout_bwd_colsum', y.data_ptr(), dy2.data_ptr(), M, N, p_drop, 1, db.data_ptr(), _stream())
             else:
                 call('pa_relu_dropout_bwd', y.data_ptr(), dy2.data_ptr(), dy2.numel(), p_drop, 1, _stream())
@@ -376,7 +410,7 @@ class Linear(Function):
             gemm_tf32(dy2, W_r, dx, M, K, N, lda=ldn, ldb=W_r.stride(0), ldc=K, b_mn=True, round_out=round_dx)
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1]:
-            dW = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
+            dW = _zeros((N, K), dy.device)
             tiles = ((N + 127) // 128) * ((K + 255) // 256 if K % 256 == 0 else (K + 127) // 128)
             gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
