@@ -671,24 +671,44 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDP + buf * C::BQ + c0, rd);
           tc::tmem_ld_wait();
           TRACE(trole, 3);
+          // rows of masked keys produce P = dS = 0; a tile below the causal diagonal needs no per-element test
+          if (!k_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float mk[4];
+            for (int c = 0; c < 32; ++c) { rs[c] = 0u; rd[c] = 0u; }
+          } else if (!diag) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
-            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);     // per-query stats, 4 columns at a time
-            const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
-            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
+            for (int c = 0; c < 32; c += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);     // per-query stats, 4 columns at a time
+              const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
+              const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int qq = c0 + c + e;
-              float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, -lq[e]);
-              if (!k_ok || (diag && kj > q0 + qq)) v = -INFINITY;
-              const float pr = fast_exp2(v);
-              const float pd = pr * mk[e];
-              const float ds = pr * (__uint_as_float(rd[c + e]) * mk[e] - dq4[e]);
-              rs[c + e] = __float_as_uint(tf32_rn(pd));
-              rd[c + e] = __float_as_uint(tf32_rn(ds));
+              for (int e = 0; e < 4; ++e) {
+                const float mk = ((mw >> (c + e)) & 1u) ? ks : 0.f;
+                const float pr = fast_exp2(fmaf(__uint_as_float(rs[c + e]), p.scale_log2, -lq[e]));
+                const float ds = pr * fmaf(__uint_as_float(rd[c + e]), mk, -dq4[e]);
+                rs[c + e] = tf32_rn_finite_bits(pr * mk);
+                rd[c + e] = tf32_rn_finite_bits(ds);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              float mk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
+              const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);
+              const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
+              const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int qq = c0 + c + e;
+                float v = fmaf(__uint_as_float(rs[c + e]), p.scale_log2, -lq[e]);
+                if (kj > q0 + qq) v = -INFINITY;
+                const float pr = fast_exp2(v);
+                const float ds = pr * fmaf(__uint_as_float(rd[c + e]), mk[e], -dq4[e]);
+                rs[c + e] = tf32_rn_finite_bits(pr * mk[e]);
+                rd[c + e] = tf32_rn_finite_bits(ds);
+              }
             }
           }
           TRACE(trole, 4);

@@ -209,21 +209,36 @@ __global__ void __launch_bounds__(NT) attn_fwd_simt_kernel(pa_attn_fwd_args A) {
 }
 
 // delta[b,h,i] = sum_c dO[b,i,h,c] * O[b,i,h,c]
-__global__ void attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ d_o, int64_t ldo, int B, int H, int Lq, int dh,
-                                  float* __restrict__ delta) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)B * Lq * H) return;
-  int h = (int)(idx % H);
-  int64_t bi = idx / H;
-  int i = (int)(bi % Lq), b = (int)(bi / Lq);
-  const float4* po = reinterpret_cast<const float4*>(o + bi * ldo + h * dh);
-  const float4* pd = reinterpret_cast<const float4*>(d_o + bi * ldo + h * dh);
+// delta[b,h,i] = sum_c O[b,i,h,c] * dO[b,i,h,c].  HBM-bound (reads O and dO once): four lanes share one (row, head)
+// slice so that a warp keeps 8 x 16-byte loads per lane in flight over fully coalesced 256/128-byte segments.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ o, const float* __restrict__ d_o, int64_t ldo, int B,
+                                                          int H, int Lq, int dh, float* __restrict__ delta) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = gid >> 2;                       // (b, i, h)
+  const int part = (int)(gid & 3);
+  const bool live = idx < (int64_t)B * Lq * H;
   float acc = 0.f;
-  for (int c = 0; c < dh / 4; ++c) {
-    float4 x = __ldg(po + c), y = __ldg(pd + c);
-    acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  int h = 0, i = 0, b = 0;
+  if (live) {
+    h = (int)(idx % H);
+    const int64_t bi = idx / H;
+    i = (int)(bi % Lq); b = (int)(bi / Lq);
+    const float4* po = reinterpret_cast<const float4*>(o + bi * ldo + h * dh);
+    const float4* pd = reinterpret_cast<const float4*>(d_o + bi * ldo + h * dh);
+    const int n4 = dh / 4;                            // 8 or 16 float4 per slice; lane `part` takes c = part, part + 4, ...
+    float4 x[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = part + 4 * u;
+      x[u] = c < n4 ? __ldg(po + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      y[u] = c < n4 ? __ldg(pd + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += x[u].x * y[u].x + x[u].y * y[u].y + x[u].z * y[u].z + x[u].w * y[u].w;
   }
-  delta[((int64_t)b * H + h) * Lq + i] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (live && part == 0) delta[((int64_t)b * H + h) * Lq + i] = acc;
 }
 
 // Recompute one 64x64 tile of P (dropped, -> Ps) and dS (-> dSs) from Q,K,V,dO tiles in smem.
@@ -395,7 +410,7 @@ int launch_bwd(const pa_attn_bwd_args& A, cudaStream_t st) {
   rc = set_smem(attn_bwd_dq_simt_kernel<DH>, smem);
   if (rc) return rc;
   int64_t n = (int64_t)A.B * A.Lq * A.H;
-  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A.o, A.d_o, A.ldo, A.B, A.H, A.Lq, A.dh, A.delta);
+  attn_delta_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, st>>>(A.o, A.d_o, A.ldo, A.B, A.H, A.Lq, A.dh, A.delta);
   PA_CHECK_LAUNCH();
   dim3 gk((A.Lk + BN - 1) / BN, A.H, A.B);
   attn_bwd_dkdv_simt_kernel<DH><<<gk, NT, smem, st>>>(A);
@@ -413,7 +428,7 @@ int pa_attn_bwd_tc(const pa_attn_bwd_args* a, void* stream);  // attn_bwd_tc.cu
 
 int pa_attn_delta_launch(const float* o, const float* d_o, int64_t ldo, int B, int H, int Lq, int dh, float* delta, cudaStream_t st) {
   int64_t n = (int64_t)B * Lq * H;
-  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(o, d_o, ldo, B, H, Lq, dh, delta);
+  attn_delta_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, st>>>(o, d_o, ldo, B, H, Lq, dh, delta);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

@@ -376,7 +376,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int c0 = 0; c0 < HC; c0 += 32) {
           uint32_t r[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(tf32_rn(s[c0 + c]));
+          for (int c = 0; c < 32; ++c) r[c] = tf32_rn_finite_bits(s[c0 + c]);      // P is in [0, 1]
           tc::tmem_st_32x32(s_addr + c0, r);
         }
         tc::tmem_st_wait();
