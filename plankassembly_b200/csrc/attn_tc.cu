@@ -58,11 +58,11 @@ template <int DH> struct Cfg {
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kTileBytes;
   static constexpr int kOffV = kOffK + kKStages * kTileBytes;
-  static constexpr int kOffBias = kOffV + kVStages * kTileBytes;
-  static constexpr int kOffXch = kOffBias + 2 * BKV * 4;     // [2 bufs x 2 halves + 2][128] floats: max / sum exchange
-  static constexpr int kOffFlag = kOffXch + 6 * BQ * 4;
-  static constexpr int kOffBar = kOffFlag + 64;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kOffXch = kOffV + kVStages * kTileBytes;    // [2 bufs x 2 halves + 2][128] floats: max / sum exchange
+  static constexpr int kOffFlag = kOffXch + 6 * BQ * 4;             // [2 items][64]: all 32 keys of the group valid
+  static constexpr int kOffBar = kOffFlag + 512;
+  static constexpr int kOffBias = kOffBar + 256;                    // [2 items][LkPad] additive key bias, sized at launch
+  static constexpr int kSmemFixed = kOffBias + 1024;                // + 2 * LkPad * 4
   static constexpr int kTmemCols = 512;
   static constexpr int kColS = 0;                          // 2 x 128 columns  S / P
   static constexpr int kColO = 256;                        // 2 x DH columns   O_j
@@ -74,6 +74,7 @@ struct Params {
   float scale_log2;   // scale * log2(e)
   float p_drop; const uint32_t* drop_rows; int LkW;
   int q_tiles, items;
+  int LkPad;          // keys rounded up to the key tile (per-item bias table length)
   int debug;          // ablation bits for timing experiments (PLANK_B200_ATTN_DEBUG); 0 in production
 };
 
@@ -259,11 +260,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     int trace_n = 0;
     const int trole = warp == 2 ? 2 : 3;
 #endif
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    // The additive key bias and the "tile needs no masking" flags of a whole item live in a per-item smem table (two
+    // tables alternate; the next item's is written before the current item's last accumulate / read-out), so a tile
+    // costs one named barrier (the row-max exchange) only.
+    auto build_table = [&](int item, uint32_t parity) {  // additive key bias + group flags of one item
+      int b_, h_, q0_, n_;
+      item_coords(item, b_, h_, q0_, n_);
+      float* bt = bias_s + (parity & 1) * p.LkPad;
+      int* ft = flag_s + (parity & 1) * 64;
+      for (int k = tid; k < n_ * BKV; k += 256) {
+        const bool ok = k < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b_ * p.Lk + k]);
+        bt[k] = ok ? 0.f : -INFINITY;
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) ft[k >> 5] = all_ok ? 1 : 0;
+      }
+    };
+    if ((int)blockIdx.x < p.items) build_table(blockIdx.x, 0);
+    uint32_t itc = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++itc) {
       int b, h, q0, n;
       item_coords(item, b, h, q0, n);
       const int qi = q0 + row;
       const int64_t row_global = ((int64_t)(b * p.H + h) * p.Lq + qi);
+      const float* bias_it = bias_s + (itc & 1) * p.LkPad;
+      const int* flag_it = flag_s + (itc & 1) * 64;
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
       float o_acc[32];
 #pragma unroll
@@ -288,33 +308,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ++oc;
       };
 
-      // Global loads on this path (key-padding bytes, dropout words) are issued a tile ahead / at the top of the
-      // tile so that their ~700-cycle latency never sits on the per-tile dependent chain.
-      auto key_ok = [&](int k0n) {
-        const int kj = k0n + tid;
-        return kj < p.Lk && !(p.kpm != nullptr && p.kpm[(int64_t)b * p.Lk + kj]);
+      // the dropout words of a tile are requested one tile ahead so that their latency never sits on the per-tile chain
+      auto load_w = [&](int k0n, uint32_t (&wd)[HC / 32]) {
+#pragma unroll
+        for (int i = 0; i < HC / 32; ++i) {
+          const int wi = ((k0n + half * HC) >> 5) + i;
+          wd[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
+        }
       };
-      bool ok_pref = tid < BKV ? key_ok(0) : false;
+      uint32_t w_pref[HC / 32];
+      if (p.p_drop > 0.f) load_w(0, w_pref);
+      TIMED_WAIT(0, asm volatile("bar.sync 1, 256;" ::: "memory"));      // the item's bias table is complete
       for (int j = 0; j < n; ++j) {
         const int buf = sc & 1;
         const int k0 = j * BKV;
         TRACE(trole, 0);
-        if (tid < BKV) {  // additive key bias for this tile: 0 or -inf (padding keys, keys beyond Lk)
-          const bool ok = ok_pref;
-          bias_s[buf * BKV + tid] = ok ? 0.f : -INFINITY;
-          const bool all_ok = __all_sync(0xffffffffu, ok);
-          if (lane == 0) flag_s[buf * 4 + (tid >> 5)] = all_ok ? 1 : 0;
-          if (j + 1 < n) ok_pref = key_ok(k0 + BKV);
-        }
         uint32_t w[HC / 32];                   // keep-bits of this row's 64 keys (precomputed Philox bit plane)
-        if (p.p_drop > 0.f) {
 #pragma unroll
-          for (int i = 0; i < HC / 32; ++i) {
-            const int wi = ((k0 + half * HC) >> 5) + i;
-            w[i] = (qi < p.Lq && wi < p.LkW) ? __ldg(p.drop_rows + row_global * p.LkW + wi) : 0u;
-          }
-        }
-        TIMED_WAIT(0, asm volatile("bar.sync 1, 256;" ::: "memory"));
+        for (int i = 0; i < HC / 32; ++i) w[i] = w_pref[i];
+        if (p.p_drop > 0.f && j + 1 < n) load_w(k0 + BKV, w_pref);
         TRACE(trole, 1);
         TIMED_WAIT(1, tc::mbar_wait(s_full + buf, (sc >> 1) & 1));
         TRACE(trole, 2);
@@ -337,7 +349,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         TRACE(trole, 3);
         const bool diag = p.causal && (k0 + BKV - 1 > q0);
         // fast path: every key of the tile is valid and no causal boundary crosses it -> no per-element masking
-        const bool clean = !diag && (flag_s[buf * 4] & flag_s[buf * 4 + 1] & flag_s[buf * 4 + 2] & flag_s[buf * 4 + 3]);
+        const int fg = k0 >> 5;
+        const bool clean = !diag && (flag_it[fg] & flag_it[fg + 1] & flag_it[fg + 2] & flag_it[fg + 3]);
         float mx = -INFINITY;                  // running in the RAW score domain; scale folded into the exp2 FFMA
         if (clean) {
 #pragma unroll
@@ -345,7 +358,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         } else {
 #pragma unroll
           for (int c = 0; c < HC; ++c) {
-            float v = s[c] + bias_s[buf * BKV + half * HC + c];
+            float v = s[c] + bias_it[k0 + half * HC + c];
             if (diag && k0 + half * HC + c > qi) v = -INFINITY;
             s[c] = v;
             mx = fmaxf(mx, v);
@@ -390,6 +403,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (j > 0) accumulate_o();        // O_{j-1}: its P V overlapped this tile's softmax
         corr_prev = corr;
       }
+      // the next item's table is built here: its key-padding loads overlap the wait for this item's last P V
+      if (item + (int)gridDim.x < p.items) build_table(item + gridDim.x, itc + 1);
       accumulate_o();
       // total row sum = sum of the two halves' partial sums
       xch_s[(4 + half) * BQ + row] = l_run;
@@ -409,9 +424,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (p.lse != nullptr && half == 0)
           p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = l_tot > 0.f ? (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
       }
-      TRACE(trole, 10);
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // xch_s (row sums) is reused by the next item
-      TRACE(trole, 11);
+      TRACE(trole, 10);   // (the next item's bias-table barrier also orders the reuse of xch_s)
     }
 #ifdef PA_ATTN_TRACE
     if (trace_on) g_attn_trace_n[trole] = trace_n;
@@ -448,14 +461,17 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.q_tiles = (a.Lq + BQ - 1) / BQ;
   p.items = p.q_tiles * a.H * a.B;
+  p.LkPad = (a.Lk + BKV - 1) / BKV * BKV;
+  const int smem_bytes = C::kSmemFixed + 2 * p.LkPad * 4;
+  if (smem_bytes > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_fwd (tc): Lk = %d too long for the bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
   auto kern = attn_fwd_tc_kernel<DH>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_done = true;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes = smem_bytes;
   }
   int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  kern<<<grid, kThreads, C::kSmem, st>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
