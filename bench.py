@@ -215,8 +215,12 @@ def run_train(args, rank, world, local_rank):
         flops_per_launch = fl * mult / calls_per_step
         avg_ms = sum(dom_ms) / len(dom_ms)
         ach = flops_per_launch / (avg_ms / 1e3) / 1e12
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the 18 calls of one step) from the
+        # committed ncu pass profiles/r1b_step_metrics.csv: pa_attn_bwd = delta + dQ + dK/dV kernels
+        traffic = {'pa_attn_bwd': 612.8e6, 'pa_attn_fwd': 187.2e6}[args.dominant] if B == 64 else None
         res['roofline'] = {'bound': 'tensor', 'kernel': args.dominant, 'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                           'frac': ach / pk['tf_sustained'], 'traffic': None, 'peak_source': pk['src'] + ' (sustained bf16)',
+                           'frac': ach / pk['tf_sustained'], 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu, profiles/r1b_step_metrics_summary.txt)',
+                           'peak_source': pk['src'] + ' (sustained bf16)',
                            'avg_launch_ms': avg_ms, 'launches_per_step': calls_per_step,
                            'share_of_step': sum(dom_ms) / ms}
     if not args.no_decode:
