@@ -10,6 +10,14 @@
 constexpr int kLnWarps = 4;
 constexpr int kLnMaxBlocks = kNumSMs * 4;
 
+// Sub-block output dropout of the residual rows: 16 random bits per element, one Philox4x32-10 call per PAIR of float4
+// chunks of a lane (chunk i uses the low halves of the four words when i is even, the high halves when it is odd).
+// Forward and backward derive the same keep-mask from (seed, offset, row, lane, i).
+__device__ __forceinline__ uint4 ln_drop_words(uint64_t seed, uint64_t offset, int64_t row, int d4, int lane, int i) {
+  return philox4x32(seed, (uint64_t)(row * (d4 / 2 + 32) + lane + (i >> 1) * 32), offset);
+}
+__device__ __forceinline__ uint32_t ln_half(uint32_t w, int i) { return (i & 1) ? (w >> 16) : (w & 0xffffu); }
+
 template <int NV>  // float4 per lane; d = NV*128
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ abias,
                                                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
@@ -18,11 +26,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32;
   const float inv_d = 1.f / (float)(NV * 128);
-  const uint32_t thr = drop_threshold(p_drop);
+  const uint32_t thr = drop_threshold16(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
     float4 v[NV];
     float sum = 0.f;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = lane + i * 32;
@@ -34,11 +43,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
           av.x += bb.x; av.y += bb.y; av.z += bb.z; av.w += bb.w;
         }
         if (p_drop > 0.f) {
-          uint4 r = philox4x32(seed, (uint64_t)(row * d4 + c), offset);
-          av.x = r.x >= thr ? av.x * keep_scale : 0.f;
-          av.y = r.y >= thr ? av.y * keep_scale : 0.f;
-          av.z = r.z >= thr ? av.z * keep_scale : 0.f;
-          av.w = r.w >= thr ? av.w * keep_scale : 0.f;
+          if ((i & 1) == 0) r = ln_drop_words(seed, offset, row, d4, lane, i);
+          av.x = ln_half(r.x, i) >= thr ? av.x * keep_scale : 0.f;
+          av.y = ln_half(r.y, i) >= thr ? av.y * keep_scale : 0.f;
+          av.z = ln_half(r.z, i) >= thr ? av.z * keep_scale : 0.f;
+          av.w = ln_half(r.w, i) >= thr ? av.w * keep_scale : 0.f;
         }
         v[i].x += av.x; v[i].y += av.y; v[i].z += av.z; v[i].w += av.w;
       }
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32, d = NV * 128;
   const float inv_d = 1.f / (float)d;
-  const uint32_t thr = drop_threshold(p_drop);
+  const uint32_t thr = drop_threshold16(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   float4 dg[NV], db[NV], dab[NV];      // dab: column sums of da = gradient of the folded linear bias
 #pragma unroll
@@ -102,6 +111,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
     }
     c1 = warp_sum(c1) * inv_d;
     c2 = warp_sum(c2) * inv_d;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = lane + i * 32;
@@ -113,11 +123,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
       dx[row * d4 + c] = o;
       if (da != nullptr) {
         if (p_drop > 0.f) {
-          uint4 r = philox4x32(seed, (uint64_t)(row * d4 + c), offset);
-          o.x = r.x >= thr ? o.x * keep_scale : 0.f;
-          o.y = r.y >= thr ? o.y * keep_scale : 0.f;
-          o.z = r.z >= thr ? o.z * keep_scale : 0.f;
-          o.w = r.w >= thr ? o.w * keep_scale : 0.f;
+          if ((i & 1) == 0) r = ln_drop_words(seed, offset, row, d4, lane, i);
+          o.x = ln_half(r.x, i) >= thr ? o.x * keep_scale : 0.f;
+          o.y = ln_half(r.y, i) >= thr ? o.y * keep_scale : 0.f;
+          o.z = ln_half(r.z, i) >= thr ? o.z * keep_scale : 0.f;
+          o.w = ln_half(r.w, i) >= thr ? o.w * keep_scale : 0.f;
         }
         da[row * d4 + c] = round_da ? tf32_rn4(o) : o;
         if (want_dabias) { dab[i].x += o.x; dab[i].y += o.y; dab[i].z += o.z; dab[i].w += o.w; }
