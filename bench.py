@@ -1,13 +1,14 @@
 """bench.py -- shape-program tokens/sec of the PlankAssembly hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload train|decode]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--decode-drawings D] [--no-decode]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one synthetic batch:
   train  (default, BASELINE.json configs[1]): full model d=512 6+6 layers, per-GPU batch 64,
          S=512 encoder / T=256 decoder positions, configured dropout 0.2, forward + backward +
          gradient all-reduce (N>1) + Adam.  tokens = decoder positions B*T (the "shape program").
-  decode (configs[2]): KV-cached greedy decode of 64 drawings, max_len 256; tokens = generated.
+  decode (configs[2], nested under "decode"): KV-cached greedy decode of D drawings per GPU in batches of 64, max_len 256
+         (default D = 128; BASELINE names 1000); tokens = generated positions.
 Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the same metric through
 the public PlankModel API with pinned HOST batches copied in and the loss read back every step.
 `--impl reference` times the CPU port of the reference (oracle/plank_oracle.py, see DESIGN.md for
@@ -181,15 +182,34 @@ def run_train(args, rank, world, local_rank):
     launches = _lib.launch_count() - l0
     dom_ms = [a.elapsed_time(b) for a, b in dom_events]
 
-    # --- end to end through the public API: pinned host batch -> device, loss read back, every step
+    # --- end to end through the public API: pinned host batch -> device, result (loss, accuracy) copied back to pinned host
+    # memory EVERY step.  The host consumes step i's numbers while step i+1 is already queued (the copy lands in a pinned ring
+    # slot guarded by an event), as a training loop that logs its loss does; the last step's result is awaited inside the
+    # timed region.
+    ring = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    ring_ev = [torch.cuda.Event() for _ in range(2)]
+    seen = []
+
     def e2e_step(i):
         hb = host[i % n_host]
         batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
         out = step(batch)
-        return float(out['loss'].item()) + float(out['accuracy'].item())
+        slot = i % 2
+        ring[slot].copy_(torch.stack([out['loss'].detach(), out['accuracy'].detach()]), non_blocking=True)
+        ring_ev[slot].record()
+        if i > 0:                                      # read the PREVIOUS step's result (its copy has certainly landed or is awaited here)
+            ring_ev[1 - slot].synchronize()
+            seen.append(ring[1 - slot].tolist())
+        if i == args.steps - 1:                        # ... and the last one before the clock stops
+            ring_ev[slot].synchronize()
+            seen.append(ring[slot].tolist())
 
-    e2e_step(0)
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    seen.clear()
     ms_e2e = timed(e2e_step, args.steps)
+    assert len(seen) == args.steps and all(x[0] == x[0] for x in seen), 'e2e: every step must deliver a finite loss to the host'
 
     tokens = B * T * world
     res = {
@@ -200,6 +220,7 @@ def run_train(args, rank, world, local_rank):
                                f'per-GPU batch {B}, S={S} encoder / T={T} decoder positions, fwd+bwd+allreduce+Adam',
                    'global_batch': B * world, 'parallelism': f'dp{world}', 'attention': model.attn_impl,
                    'l2': 'per-step activations (>3 GB) exceed the 126 MB L2; no explicit flush',
+                   'e2e': 'pinned H2D of every batch + D2H of (loss, accuracy) every step; the host reads step i while step i+1 runs',
                    'encoder_tokens_per_step': B * S * world},
         'clocks': clk.summary,
         'e2e': {'value': tokens * args.steps / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8},
@@ -224,16 +245,26 @@ def run_train(args, rank, world, local_rank):
                            'avg_launch_ms': avg_ms, 'launches_per_step': calls_per_step,
                            'share_of_step': sum(dom_ms) / ms}
     if not args.no_decode:
-        res['decode'] = run_decode(model, cfg, host, resident, dev, world, timed)
+        res['decode'] = run_decode(model, cfg, host, resident, dev, world, rank, timed, args.decode_drawings)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res['cpu_baseline'] = cpu_baseline_train(sample_batch=2, steps=1)
     return res
 
 
-def run_decode(model, cfg, host, resident, dev, world, timed, reps=2):
-    """BASELINE configs[2]: KV-cached greedy decode, per-GPU batch of drawings, max_len = MAX_OUTPUT_LENGTH.
-    tokens = generated positions (every row decodes until all rows have emitted END, as the reference does)."""
+def run_decode(model, cfg, host, resident, dev, world, rank, timed, n_drawings):
+    """BASELINE configs[2]: KV-cached greedy decode of `n_drawings` synthetic drawings per GPU in batches of the bench batch
+    size, max_len = MAX_OUTPUT_LENGTH (`--decode-drawings 1000` is the configuration BASELINE.json names).
+    tokens = generated positions (every row decodes until all rows of its batch have emitted END, as the reference does)."""
     from plankassembly_b200 import synthetic as syn
+    B = resident[0]['input_value'].shape[0]
+    n_batches = max(1, (n_drawings + B - 1) // B)
+    host, resident = list(host), list(resident)
+    while len(host) < n_batches:                           # more drawings than the train loop's four batches
+        i = len(host)
+        hb = syn.batch_for(cfg, range((rank * 64 + i) * B + 100000, (rank * 64 + i + 1) * B + 100000))
+        hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in hb.items()}
+        host.append(hb)
+        resident.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()})
     # decode with the seeded-init weights (the timed train steps above have moved `model`'s weights; a
     # half-trained model may emit END everywhere at once, which would stop the loop after one step)
     model.load_state_dict(syn.init_state_dict(cfg))
@@ -243,20 +274,20 @@ def run_decode(model, cfg, host, resident, dev, world, timed, reps=2):
         n_tok = [0]
 
         def dec(i):
-            o = model(resident[i % len(resident)])
+            o = model(resident[i % n_batches])
             n_tok[0] += o['samples'].numel()
 
-        ms = timed(dec, reps)
+        ms = timed(dec, n_batches)
         tok_resident = n_tok[0] * world
         n_tok[0] = 0
 
         def dec_e2e(i):
-            hb = host[i % len(host)]
+            hb = host[i % n_batches]
             batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
             o = model(batch)
             n_tok[0] += o['samples'].cpu().numel() + o['attach'].cpu().numel() * 0
 
-        ms_e2e = timed(dec_e2e, reps)
+        ms_e2e = timed(dec_e2e, n_batches)
     model.train()
     B, T = out['samples'].shape
     d, S, L = cfg.MODEL.NUM_MODEL, cfg.DATA.MAX_INPUT_LENGTH - 1, cfg.MODEL.NUM_DECODER_LAYERS
@@ -265,7 +296,8 @@ def run_decode(model, cfg, host, resident, dev, world, timed, reps=2):
     gbs = bytes_tok * tok_resident / world / (ms / 1e3) / 1e9
     pk = peaks()
     return {'metric': 'greedy-decode generated tokens/sec (KV cache, CUDA-graph step)', 'value': tok_resident / (ms / 1e3),
-            'unit': UNIT, 'ms_per_decode': ms / reps, 'batch_per_gpu': B, 'steps_per_decode': T,
+            'unit': UNIT, 'ms_per_decode': ms / n_batches, 'batch_per_gpu': B, 'drawings_per_gpu': n_batches * B, 'steps_per_decode': T,
+            'engine': getattr(model._decoder_engine, 'mode', None),
             'e2e': {'value': n_tok[0] * world / (ms_e2e / 1e3), 'unit': UNIT},
             'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
                          'note': 'algorithmic fp32 K/V bytes per token (cross + mean self cache) / measured time per GPU'}}
@@ -309,6 +341,7 @@ def main():
     ap.add_argument('--dominant', default='pa_attn_bwd', choices=['pa_attn_fwd', 'pa_attn_bwd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--decode-drawings', type=int, default=128, help='drawings per GPU in the greedy-decode leg (BASELINE configs[2]: 1000)')
     ap.add_argument('--profile-decode', action='store_true', help='bracket one greedy decode with cudaProfilerStart/Stop and exit')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE step with cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit')
     args = ap.parse_args()
