@@ -54,6 +54,7 @@ struct BwdParams {
   float p_drop; const uint32_t* drop_rows; const uint32_t* drop_cols; int LkW, LqW;
   float* dbias;          // [3*H*DH] += column sums of dq | dk | dv (in-projection bias gradient), may be NULL
   int tiles, items;
+  int wide_st;           // outputs are 32-byte aligned with row pitches that are multiples of 8 floats: 256-bit stores
   int LkPad;             // keys rounded up to the key tile (per-item bias table length)
   int LqPad;             // queries rounded up to the query tile (per-item lse/delta table length)
   int trace;
@@ -384,11 +385,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tc::tmem_ld_wait();
         if (q_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 32; c += 8) {
             float4 v = make_float4(__uint_as_float(r[c]) * p.scale, __uint_as_float(r[c + 1]) * p.scale,
                                    __uint_as_float(r[c + 2]) * p.scale, __uint_as_float(r[c + 3]) * p.scale);
-            if (p.round_out) v = tf32_rn4(v);
-            *reinterpret_cast<float4*>(out + c0 + c) = v;
+            float4 w = make_float4(__uint_as_float(r[c + 4]) * p.scale, __uint_as_float(r[c + 5]) * p.scale,
+                                   __uint_as_float(r[c + 6]) * p.scale, __uint_as_float(r[c + 7]) * p.scale);
+            if (p.round_out) { v = tf32_rn4(v); w = tf32_rn4(w); }
+            if (p.wide_st) st_global_v8(out + c0 + c, v, w);
+            else { *reinterpret_cast<float4*>(out + c0 + c) = v; *reinterpret_cast<float4*>(out + c0 + c + 4) = w; }
           }
         }
         if (p.dbias != nullptr) {          // q-bias gradient: column sums over this warp's 32 query rows
@@ -735,18 +739,28 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDK + c0, rk);
         tc::tmem_ld_32x32(tmem_base + lane_addr + C::kColDV + c0, rv);
         tc::tmem_ld_wait();
+        TRACE(trole, 14);
         if (row_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 32; c += 8) {
             float4 a = make_float4(__uint_as_float(rk[c]) * p.scale, __uint_as_float(rk[c + 1]) * p.scale,
                                    __uint_as_float(rk[c + 2]) * p.scale, __uint_as_float(rk[c + 3]) * p.scale);
+            float4 a2 = make_float4(__uint_as_float(rk[c + 4]) * p.scale, __uint_as_float(rk[c + 5]) * p.scale,
+                                    __uint_as_float(rk[c + 6]) * p.scale, __uint_as_float(rk[c + 7]) * p.scale);
             float4 v = make_float4(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]), __uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3]));
-            if (n == 0) { a = make_float4(0.f, 0.f, 0.f, 0.f); v = a; }
-            if (p.round_out) { a = tf32_rn4(a); v = tf32_rn4(v); }
-            *reinterpret_cast<float4*>(outk + c0 + c) = a;
-            *reinterpret_cast<float4*>(outv + c0 + c) = v;
+            float4 v2 = make_float4(__uint_as_float(rv[c + 4]), __uint_as_float(rv[c + 5]), __uint_as_float(rv[c + 6]), __uint_as_float(rv[c + 7]));
+            if (n == 0) { a = make_float4(0.f, 0.f, 0.f, 0.f); a2 = a; v = a; v2 = a; }
+            if (p.round_out) { a = tf32_rn4(a); a2 = tf32_rn4(a2); v = tf32_rn4(v); v2 = tf32_rn4(v2); }
+            if (p.wide_st) {
+              st_global_v8(outk + c0 + c, a, a2);
+              st_global_v8(outv + c0 + c, v, v2);
+            } else {
+              *reinterpret_cast<float4*>(outk + c0 + c) = a; *reinterpret_cast<float4*>(outk + c0 + c + 4) = a2;
+              *reinterpret_cast<float4*>(outv + c0 + c) = v; *reinterpret_cast<float4*>(outv + c0 + c + 4) = v2;
+            }
           }
         }
+        TRACE(trole, 15);
         if (p.dbias != nullptr) {          // k- and v-bias gradients: column sums over this warp's 32 key rows
           float ck[32], cv[32];
           const bool use = row_ok && n > 0;
@@ -784,6 +798,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols; p.dbias = a.dbias;
   p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
+  p.wide_st = ((((uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 31) == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0) ? 1 : 0;
 #ifdef PA_ATTN_TRACE
   { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & (1024 | 2048)) : 0; }
 #endif

@@ -74,6 +74,7 @@ struct Params {
   float scale_log2;   // scale * log2(e)
   float p_drop; const uint32_t* drop_rows; int LkW;
   int q_tiles, items;
+  int wide_st;        // o is 32-byte aligned with a row pitch that is a multiple of 8 floats: 256-bit stores
   int LkPad;          // keys rounded up to the key tile (per-item bias table length)
   int debug;          // ablation bits for timing experiments (PLANK_B200_ATTN_DEBUG); 0 in production
 };
@@ -415,10 +416,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (has_o) {
           float* op = p.o + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + half * 32;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 32; c += 8) {
             float4 v = make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-            if (p.round_out) v = tf32_rn4(v);
-            *reinterpret_cast<float4*>(op + c) = v;
+            float4 w = make_float4(o_acc[c + 4] * inv, o_acc[c + 5] * inv, o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+            if (p.round_out) { v = tf32_rn4(v); w = tf32_rn4(w); }
+            if (p.wide_st) st_global_v8(op + c, v, w);
+            else { *reinterpret_cast<float4*>(op + c) = v; *reinterpret_cast<float4*>(op + c + 4) = w; }
           }
         }
         if (p.lse != nullptr && half == 0)
@@ -462,6 +465,7 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   p.q_tiles = (a.Lq + BQ - 1) / BQ;
   p.items = p.q_tiles * a.H * a.B;
   p.LkPad = (a.Lk + BKV - 1) / BKV * BKV;
+  p.wide_st = (((uintptr_t)a.o & 31) == 0 && a.ldo % 8 == 0) ? 1 : 0;
   const int smem_bytes = C::kSmemFixed + 2 * p.LkPad * 4;
   if (smem_bytes > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_fwd (tc): Lk = %d too long for the bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
   auto kern = attn_fwd_tc_kernel<DH>;

@@ -56,6 +56,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 256-bit global store (sm_100+): p must be 32-byte aligned.  The tensor-core kernels read accumulators out of TMEM as
+// (lane = row, registers = consecutive columns), so each lane writes its own 128-byte row segment; the LSU works per
+// touched line and instruction, and the wide form halves the number of store instructions.
+__device__ __forceinline__ void st_global_v8(float* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,7 +19,7 @@ n = (ctypes.c_int * 4)()
 assert lib.pa_debug_attn_bwd_trace(buf, n) == 0
 names = {0: {0: 'qdo_empty ok', 1: 'kv_empty ok'},
          1: {0: 'qdo_full+dq_empty ok', 1: 'kv_full ok', 2: 'S,dP issued', 3: 'ds_full ok', 4: 'dQ issued'},
-         2: {0: 'tile start', 1: 'bar', 2: 'sdp_full ok', 3: 'S,dP loaded', 4: 'math done', 5: 'dS stored', 6: 'ds_full arrive', 7: 'dq_full ok', 8: 'item end', 9: 'item start', 10: 'qdo_full ok', 11: 'Q,dO in TMEM', 12: 'bias table written', 13: 'item bar'}}
+         2: {0: 'tile start', 1: 'bar', 2: 'sdp_full ok', 3: 'S,dP loaded', 4: 'math done', 5: 'dS stored', 6: 'ds_full arrive', 7: 'dq_full ok', 8: 'item end', 9: 'item start', 10: 'qdo_full ok', 11: 'Q,dO in TMEM', 12: 'bias table written', 13: 'item bar', 14: 'acc loaded', 15: 'stores issued'}}
 names[3] = names[2]
 ev = []
 for r in range(4):
