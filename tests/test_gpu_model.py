@@ -109,6 +109,21 @@ def test_noisy_decode_matches_reference(ratio, engine, monkeypatch):
     assert ok, info
 
 
+@pytest.mark.parametrize('chains', [1, 2, 4])
+def test_fused_decode_chains_agree(chains, monkeypatch):
+    """The persistent decode kernel splits the batch into independent sub-batch chains; every split must give the same
+    tokens as the reference (stop rule: all chains go on until EVERY sequence of the batch has emitted END)."""
+    monkeypatch.setenv('PLANK_B200_DECODE', 'fused')
+    monkeypatch.setenv('PLANK_B200_DECODE_CHAINS', str(chains))
+    cfg = syn.tiny_cfg()
+    g = golden('tiny_trained_noise05')
+    batch = syn.batch_for(cfg, range(100, 108), noise_ratio=0.05)
+    m = build(cfg, trained_tiny_state_dict()).eval()
+    out = m(to_dev(batch))
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='')
+    assert ok, info
+
+
 def test_missing_input_type_key():
     """Sideface batches carry no input_type (ref trainer_sideface.py); the model must cope."""
     from plank_oracle import OraclePlankModel
