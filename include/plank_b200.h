@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 #define PA_MAX_TABLES 8
 
 enum pa_status { PA_OK = 0, PA_ERR_ARG = -1, PA_ERR_CUDA = -2, PA_ERR_UNSUPPORTED = -3 };
@@ -106,6 +106,8 @@ typedef struct {
   int round_out;               /* write O rounded to TF32 (it feeds a tensor-core GEMM) */
   const uint32_t* drop_rows;   /* keep-bit masks from pa_dropout_mask (required by impl 1 when p_drop > 0) */
   const uint32_t* drop_cols;
+  const int32_t* kv_len;       /* optional [B] (impl 1): every key j >= kv_len[b] is PAD in kpm -> whole key tiles beyond it are
+                                  skipped (ragged batches padded to a fixed length, LineDataset layout); NULL = Lk */
 } pa_attn_fwd_args;
 int pa_attn_fwd(const pa_attn_fwd_args* args, void* stream);
 
@@ -127,6 +129,7 @@ typedef struct {
   const uint32_t* drop_rows;   /* the masks the forward used */
   const uint32_t* drop_cols;
   float* dbias;                /* impl 1 only, may be NULL: [3*H*dh] += column sums of (dq | dk | dv) = in-proj bias gradient */
+  const int32_t* kv_len;       /* as in pa_attn_fwd_args */
 } pa_attn_bwd_args;
 int pa_attn_bwd(const pa_attn_bwd_args* args, void* stream);
 

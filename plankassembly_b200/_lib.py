@@ -15,7 +15,7 @@ class AttnFwdArgs(C.Structure):
                 ('o', vp), ('ldo', i64), ('lse', vp), ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
                 ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32),
-                ('drop_rows', vp), ('drop_cols', vp)]
+                ('drop_rows', vp), ('drop_cols', vp), ('kv_len', vp)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -25,7 +25,7 @@ class AttnBwdArgs(C.Structure):
                 ('kpm', vp),
                 ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32), ('dh', i32), ('causal', i32),
                 ('scale', f32), ('p_drop', f32), ('seed', u64), ('offset', u64), ('impl', i32), ('round_out', i32),
-                ('drop_rows', vp), ('drop_cols', vp), ('dbias', vp)]
+                ('drop_rows', vp), ('drop_cols', vp), ('dbias', vp), ('kv_len', vp)]
 
 
 class GemmArgs(C.Structure):
@@ -107,7 +107,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError => header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.pa_abi_version() != 1:
+    if lib.pa_abi_version() != 2:
         raise PlankB200Error('ABI version mismatch')
     _lib = lib
     return lib

@@ -54,6 +54,7 @@ struct BwdParams {
   float p_drop; const uint32_t* drop_rows; const uint32_t* drop_cols; int LkW, LqW;
   float* dbias;          // [3*H*DH] += column sums of dq | dk | dv (in-projection bias gradient), may be NULL
   int tiles, items;
+  const int32_t* kv_len; // optional [B]: keys >= kv_len[b] are all PAD -> key tiles beyond it are skipped
   int wide_st;           // outputs are 32-byte aligned with row pitches that are multiples of 8 floats: 256-bit stores
   int LkPad;             // keys rounded up to the key tile (per-item bias table length)
   int LqPad;             // queries rounded up to the query tile (per-item lse/delta table length)
@@ -115,9 +116,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   auto coords = [&](int item, int& b, int& h, int& q0, int& n) {
-    int qt = item % p.tiles, bh = item / p.tiles;
+    int bh = item / p.tiles;
+    int qt = (item % p.tiles + bh) % p.tiles;   // rotated with bh: balances causal / kv_len-shortened items over the CTAs
     h = bh % p.H; b = bh / p.H; q0 = qt * C::BQ;
-    int all = (p.Lk + C::BK - 1) / C::BK;
+    const int lk = p.kv_len != nullptr ? min(p.Lk, max(1, __ldg(p.kv_len + b))) : p.Lk;
+    int all = (lk + C::BK - 1) / C::BK;
     n = p.causal ? min(all, (q0 + C::BQ - 1) / C::BK + 1) : all;
   };
 
@@ -477,9 +480,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
 
   const int q_tiles_all = (p.Lq + C::BQ - 1) / C::BQ;
   auto coords = [&](int item, int& b, int& h, int& k0, int& i0) {
-    int kt = item % p.tiles, bh = item / p.tiles;
+    int bh = item / p.tiles;
+    int kt = (item % p.tiles + bh) % p.tiles;   // rotated with bh: balances causal / all-PAD key tiles over the CTAs
     h = bh % p.H; b = bh / p.H; k0 = kt * C::BKV;
     i0 = p.causal ? k0 / C::BQ : 0;          // first query tile that can see these keys
+    if (p.kv_len != nullptr && k0 >= __ldg(p.kv_len + b) && k0 > 0) i0 = q_tiles_all;   // a key tile of PAD only: dK = dV = 0
   };
 
   if (warp == 0) {
@@ -798,6 +803,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.p_drop = a.p_drop; p.drop_rows = a.drop_rows; p.drop_cols = a.drop_cols; p.dbias = a.dbias;
   p.LkW = (a.Lk + 31) / 32; p.LqW = (a.Lq + 31) / 32;
+  p.kv_len = a.kpm != nullptr ? a.kv_len : nullptr;
   p.wide_st = ((((uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 31) == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0) ? 1 : 0;
 #ifdef PA_ATTN_TRACE
   { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & (1024 | 2048)) : 0; }

@@ -74,6 +74,7 @@ struct Params {
   float scale_log2;   // scale * log2(e)
   float p_drop; const uint32_t* drop_rows; int LkW;
   int q_tiles, items;
+  const int32_t* kv_len;   // optional [B]: keys >= kv_len[b] are all PAD -> key tiles beyond it are skipped
   int wide_st;        // o is 32-byte aligned with a row pitch that is a multiple of 8 floats: 256-bit stores
   int LkPad;          // keys rounded up to the key tile (per-item bias table length)
   int debug;          // ablation bits for timing experiments (PLANK_B200_ATTN_DEBUG); 0 in production
@@ -124,11 +125,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   auto item_coords = [&](int item, int& b, int& h, int& q0, int& ntiles) {
-    int qt = item % p.q_tiles;
     int bh = item / p.q_tiles;
+    // rotate the tile index with bh: a CTA's successive items (stride = grid size, a multiple of 4) would otherwise all
+    // have the SAME tile index, and tiles differ in work (causal rows, key tiles skipped through kv_len)
+    int qt = (item % p.q_tiles + bh) % p.q_tiles;
     h = bh % p.H; b = bh / p.H;
     q0 = qt * BQ;
-    int all = (p.Lk + BKV - 1) / BKV;
+    const int lk = p.kv_len != nullptr ? min(p.Lk, max(1, __ldg(p.kv_len + b))) : p.Lk;
+    int all = (lk + BKV - 1) / BKV;
     ntiles = p.causal ? min(all, qt + 1) : all;
   };
 
@@ -466,6 +470,7 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   p.items = p.q_tiles * a.H * a.B;
   p.LkPad = (a.Lk + BKV - 1) / BKV * BKV;
   p.wide_st = (((uintptr_t)a.o & 31) == 0 && a.ldo % 8 == 0) ? 1 : 0;
+  p.kv_len = a.kpm != nullptr ? a.kv_len : nullptr;
   const int smem_bytes = C::kSmemFixed + 2 * p.LkPad * 4;
   if (smem_bytes > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_fwd (tc): Lk = %d too long for the bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
   auto kern = attn_fwd_tc_kernel<DH>;

@@ -229,12 +229,32 @@ def _drop_masks(B, H, Lq, Lk, p_drop, seed, off, device):
     return rows, cols
 
 
+_KV_LEN_CACHE = []      # [(kpm tensor, version, kv_len)]: one mask serves all layers of a step
+
+
+def _kv_len(kpm):
+    """[B] int32: 1 + index of the last non-PAD key (>= 1).  Batches padded to a fixed length (LineDataset layout) let the
+    tensor-core attention kernels skip whole key tiles beyond it; nothing changes numerically (those keys carry -inf)."""
+    if kpm is None:
+        return None
+    for t, ver, out in _KV_LEN_CACHE:
+        if t is kpm and ver == kpm._version:
+            return out
+    Lk = kpm.shape[1]
+    idx = torch.arange(1, Lk + 1, device=kpm.device, dtype=torch.int32)
+    out = ((kpm == 0).to(torch.int32) * idx).amax(1).clamp_(min=1).contiguous()
+    _KV_LEN_CACHE.append((kpm, kpm._version, out))
+    del _KV_LEN_CACHE[:-4]
+    return out
+
+
 def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, seed, off, impl, want_lse, device, rnd=False):
     o = torch.empty(B, Lq, H * dh, device=device, dtype=torch.float32)
     lse = torch.empty(B, H, Lq, device=device, dtype=torch.float32) if want_lse else None
     masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, device) if (impl == 1 and p_drop > 0) else (None, None)
     a = AttnFwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), H * dh, _ptr(lse), _ptr(kpm), B, H, Lq, Lk, dh, int(causal),
-                    dh ** -0.5, p_drop, seed, off, impl, int(rnd), _ptr(masks[0]), _ptr(masks[1]))
+                    dh ** -0.5, p_drop, seed, off, impl, int(rnd), _ptr(masks[0]), _ptr(masks[1]),
+                    _ptr(_kv_len(kpm)) if impl == 1 else None)
     call('pa_attn_fwd', C.byref(a), _stream())
     return o, lse, masks
 
@@ -246,7 +266,8 @@ def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, 
         masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, o.device)
     a = AttnBwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), do.data_ptr(), H * dh, lse.data_ptr(), delta.data_ptr(),
                     dq, dk, dv, lddq, lddk, lddv, _ptr(kpm), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, p_drop, seed, off, impl, int(rnd),
-                    _ptr(masks[0]), _ptr(masks[1]), _ptr(dbias) if impl == 1 else None)
+                    _ptr(masks[0]), _ptr(masks[1]), _ptr(dbias) if impl == 1 else None,
+                    _ptr(_kv_len(kpm)) if impl == 1 else None)
     call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
 
 

@@ -7,7 +7,8 @@ B, H, dh, L = 64, 8, 64, 512
 d = H * dh
 p = float(sys.argv[1]) if len(sys.argv) > 1 else 0.2
 qkv = torch.randn(B, L, 3 * d, device='cuda').requires_grad_(True)
-kpm = torch.zeros(B, L, dtype=torch.uint8, device='cuda'); kpm[:, 400:] = 1
+valid = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+kpm = torch.zeros(B, L, dtype=torch.uint8, device='cuda'); kpm[:, valid:] = 1
 w = torch.randn(B, L, d, device='cuda')
 def fwd():
     return ops.SelfAttention.apply(qkv, None, kpm, H, False, p, 1, True)
