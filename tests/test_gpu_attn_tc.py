@@ -181,3 +181,36 @@ def test_tc_bwd_dropout_matches_fp32_kernels():
     torch.cuda.synchronize()
     for a, b in zip(grads[0].split(d, -1), grads[1].split(d, -1)):
         assert rel_err(a.cpu(), b.cpu()) < BWD_TOL
+
+
+@pytest.mark.parametrize('H,dh,L,causal,valid', [(8, 64, 512, False, (5, 130, 300, 512)), (8, 64, 256, True, (1, 70, 129, 256)),
+                                                  (4, 32, 1199, False, (1199, 40, 641, 1024))])
+def test_kv_len_skips_padding_tiles(H, dh, L, causal, valid):
+    """Ragged batch padded to a fixed length (reference LineDataset layout): the kernels receive kv_len = 1 + last valid key
+    and skip whole key tiles behind it (also whole dK/dV items); forward and all three gradients against fp64 math."""
+    from plankassembly_b200 import ops
+    B = len(valid)
+    g = torch.Generator().manual_seed(31)
+    d = H * dh
+    qkv = tf32_round(torch.randn(B, L, 3 * d, generator=g)).requires_grad_(True)
+    kpm = torch.zeros(B, L, dtype=torch.bool)
+    for b, n in enumerate(valid):
+        kpm[b, n:] = True
+    ck = kpm.cuda().view(torch.uint8)
+    assert ops._kv_len(ck).tolist() == [min(n, L) for n in valid]
+    q64 = qkv.detach().double().cpu().requires_grad_(True)
+    q, k, v = q64.split(d, -1)
+    ref = attn_ref(q, k, v, kpm, causal, H)
+    w = tf32_round(torch.randn(B, L, d, generator=g))
+    (ref * w.double().cpu()).sum().backward()
+    out = ops.SelfAttention.apply(qkv, None, ck, H, causal, 0.0, 1)
+    (out * w).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu(), ref.detach()) < TOL
+    gq, gk, gv = qkv.grad.cpu().split(d, -1)
+    rq, rk, rv = q64.grad.split(d, -1)
+    for name, a, b_ in (('dq', gq, rq), ('dk', gk, rk), ('dv', gv, rv)):
+        assert rel_err(a, b_) < BWD_TOL, name
+    # gradients of PAD keys are exactly zero (their dK/dV items are skipped, not computed)
+    for b, n in enumerate(valid):
+        assert gk[b, n:].abs().max().item() == 0.0 if n < L else True
