@@ -33,13 +33,19 @@ __global__ void __launch_bounds__(128) dropout_mask_kernel(uint32_t* __restrict_
     rows[rg * LkW + kw] = word;
   }
   if (cols != nullptr) {
-    uint32_t mine = 0;
+    // 32x32 bit-matrix transpose across the warp (lane = query, bit = key  ->  lane = key, bit = query) in five
+    // shuffle stages instead of 32 ballots: stage j swaps the off-diagonal j x j blocks of every 2j x 2j block.
+    uint32_t w = word;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const uint32_t t = __ballot_sync(0xffffffffu, (word >> k) & 1u);   // bit q%32 of key kw*32+k
-      if (lane == k) mine = t;
+    for (int j = 16; j >= 1; j >>= 1) {
+      // m selects the bit positions whose bit j is clear: 0x0000FFFF, 0x00FF00FF, 0x0F0F0F0F, 0x33333333, 0x55555555
+      const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, w, j);
+      // lanes with bit j clear keep their low-j columns and take the partner's low-j columns as their high ones;
+      // lanes with bit j set keep their high-j columns and take the partner's high ones as their low ones
+      w = (lane & j) ? ((w & ~m) | ((other >> j) & m)) : ((w & m) | ((other << j) & ~m));
     }
-    cols[((int64_t)bh * (LkW * 32) + kw * 32 + lane) * LqW + qb] = mine;
+    cols[((int64_t)bh * (LkW * 32) + kw * 32 + lane) * LqW + qb] = w;     // bit q%32 of key kw*32+lane
   }
 }
 
