@@ -21,6 +21,23 @@
 #include <mutex>
 #include <stdlib.h>
 
+// Debug timeline (PLANK_B200_NVCC_FLAGS=-DPA_GEMM_TRACE, PLANK_B200_GEMM_DEBUG bit 8): clock64 per event of CTA 0
+// (roles: 0 TMA producer, 1 MMA issuer, 2 epilogue warp 2); read back with pa_debug_gemm_trace().
+#ifdef PA_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[3][2048];
+__device__ int g_gemm_trace_n[3];
+#define GTRACE(role, ev)                                                                          \
+  do {                                                                                           \
+    if (gtrace_on && gtrace_n < 2048) g_gemm_trace[role][gtrace_n++] = ((unsigned long long)(ev) << 56) | (clock64() & 0xffffffffffffffull); \
+  } while (0)
+#define GTRACE_DECL(cond) const bool gtrace_on = (p.debug & 8) && blockIdx.x == 0 && (cond); int gtrace_n = 0
+#define GTRACE_END(role) do { if (gtrace_on) g_gemm_trace_n[role] = gtrace_n; } while (0)
+#else
+#define GTRACE(role, ev) do {} while (0)
+#define GTRACE_DECL(cond) do {} while (0)
+#define GTRACE_END(role) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -107,12 +124,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      GTRACE_DECL(true);
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int b, mt, nt, kb0, kb1;
         decode(tile, b, mt, nt, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(empty_bar + stage, phase ^ 1);
+          GTRACE(0, 0);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
           tc::mbar_arrive_expect_tx(full_bar + stage, C::kStageBytes);
@@ -143,6 +162,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      GTRACE_END(0);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
@@ -150,16 +170,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~70 cycles).
     {
       constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      GTRACE_DECL(lane == 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int b, mt, nt, kb0, kb1;
         decode(tile, b, mt, nt, kb0, kb1);
         tc::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        GTRACE(1, 0);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(full_bar + stage, phase);
+          GTRACE(1, 1);
           tc::tc_fence_after();
           const uint32_t sa = tc::smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
@@ -179,11 +202,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (kb + 1 == kb1) tc::tc_commit(tmem_full + acc);                  // accumulator complete -> epilogue
           }
           __syncwarp();
+          GTRACE(1, 2);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (kb0 >= kb1) { if (tc::elect_one()) tc::tc_commit(tmem_full + acc); __syncwarp(); }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      GTRACE_END(1);
     }
   } else {
     // ===================================== epilogue =========================================
@@ -192,6 +217,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    GTRACE_DECL(warp == 2 && lane == 0);
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       int b, mt, nt, kb0, kb1;
       decode(tile, b, mt, nt, kb0, kb1);
@@ -202,12 +228,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (et < BN) bias_s[et] = (nt * BN + et < p.N) ? __ldg(p.bias + nt * BN + et) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      GTRACE(2, 0);
       tc::mbar_wait(tmem_full + acc, acc_phase);
+      GTRACE(2, 1);
       tc::tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       float* crow = p.c + (int64_t)b * p.c_batch_stride + (int64_t)row * p.ldc;
-      uint8_t* my_stage = out_stage + (warp - 2) * (32 * 128);
 #pragma unroll 1
       for (int c0 = half * 32; c0 < ((p.debug & 1) ? 0 : BN); c0 += 64) {
         uint32_t r[32];
@@ -221,8 +248,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int col0 = nt * BN + c0;
         if (p.tma_store) {
           if (kb1 > kb0 && col0 < p.N) {        // warp-uniform
+            uint8_t* my_stage = out_stage + (warp - 2) * (32 * 128);
+            // (two alternating slots per warp were tried: the ~2700-cycle wait moves into the TMA queue, no gain)
             if (lane == 0 && !(p.debug & 2)) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
             __syncwarp();
+            GTRACE(2, 2);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int col = col0 + j;
@@ -294,8 +324,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+      GTRACE(2, 3);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    GTRACE_END(2);
   }
   if (p.tma_store && warp >= 2 && lane == 0) tc::tma_store_wait_all();
   tc::tc_fence_before();
@@ -379,6 +411,14 @@ int launch(const pa_gemm_args& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef PA_GEMM_TRACE
+extern "C" int pa_debug_gemm_trace(unsigned long long* out_host /*[3][2048]*/, int* n_host /*[3]*/) {
+  PA_CUDA(cudaMemcpyFromSymbol(out_host, g_gemm_trace, sizeof(unsigned long long) * 3 * 2048));
+  PA_CUDA(cudaMemcpyFromSymbol(n_host, g_gemm_trace_n, sizeof(int) * 3));
+  return PA_OK;
+}
+#endif
 
 int pa_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                     uint32_t box_inner, uint32_t box_outer, bool atom32) {

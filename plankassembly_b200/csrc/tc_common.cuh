@@ -89,6 +89,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread have finished READING their smem source (two alternating staging slots)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // One lane of a fully converged warp (the role loops of the MMA warps stay warp-uniform and only the tcgen05.mma /
