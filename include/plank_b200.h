@@ -82,7 +82,8 @@ int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
  * q[(b*Lq+i)*ldq + h*dh + c] etc., so the packed in-proj output [B,L,3d] is consumed in place.
  * kpm: [B,Lk] uint8, 1 = PAD key (NULL = none); causal: key j visible to query i iff j <= i.
  * lse: [B,H,Lq] natural-log sum-exp of the masked scaled scores (saved for bwd; may be NULL).
- * impl: 0 = fp32 SIMT (exact mode), 1 = tcgen05 TF32 tensor-core path. */
+ * impl: 0 = fp32 SIMT (exact mode), 1 = tcgen05 TF32 tensor-core path (dh 32 or 64; Lk <= 2048 and, for the backward,
+ * Lq <= 1280: per-item bias / statistics tables live in shared memory; longer sequences return PA_ERR_UNSUPPORTED). */
 /* Attention-probability dropout keep-masks for the tensor-core kernels, generated ONCE per attention call
  * (all warps of the chip) instead of three times inside the forward / dQ / dK-dV kernels (4 warps per SM):
  * 16 random bits per score: bit = half-word k%2 of word (k%8)/2 of Philox4x32-10(seed, counter = (bh*Lq + q)*ceil(Lk/8)
