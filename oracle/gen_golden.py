@@ -14,6 +14,7 @@ Cases
   tiny_trained  same model overfit on 10 synthetic drawings (weights committed as fp16)
   config1_init  BASELINE config 1: d=256 H=8 ff=1024 L=2+2 S=1199 T=128 B=4, seeded init
   config2_init  BASELINE config 2 model (d=512, 6+6) at B=2, S=512, T=256, seeded init
+  config4_init  BASELINE config 4 shapes (train_visible.yaml: S=999, T=128, full model) at B=2, seeded init
 """
 from __future__ import annotations
 
@@ -139,9 +140,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
     ap.add_argument('--skip-train', action='store_true')
+    ap.add_argument('--only', default=None, help='generate just this case (e.g. config4_init)')
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if args.only == 'config4_init':
+        c4 = syn.config4(dropout=0.0)
+        run_case('config4_init', c4, syn.init_state_dict(c4), range(2), args.out)
+        return
 
     tiny = syn.tiny_cfg()
     run_case('tiny_init', tiny, syn.init_state_dict(tiny), range(4), args.out)
@@ -164,6 +170,8 @@ def main():
     run_case('config1_init', c1, syn.init_state_dict(c1), range(4), args.out)
     c2 = syn.config2(dropout=0.0)
     run_case('config2_init', c2, syn.init_state_dict(c2), range(2), args.out)
+    c4 = syn.config4(dropout=0.0)
+    run_case('config4_init', c4, syn.init_state_dict(c4), range(2), args.out)
 
 
 if __name__ == '__main__':

@@ -13,6 +13,7 @@ CASES = {
     'tiny_trained': (syn.tiny_cfg, 'trained'),
     'config1_init': (syn.config1, 'init'),
     'config2_init': (lambda: syn.config2(dropout=0.0), 'init'),
+    'config4_init': (lambda: syn.config4(dropout=0.0), 'init'),      # train_visible.yaml shapes: S=999, T=128
 }
 
 

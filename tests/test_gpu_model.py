@@ -35,7 +35,7 @@ def precision(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init'])
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init', 'config4_init'])
 def test_train_step_matches_reference(name, precision):
     cfg, sd, batch, g = case(name)
     m = build(cfg, sd).train()
@@ -82,7 +82,7 @@ def test_forward_returns_reference_shaped_dict():
 
 
 @pytest.mark.parametrize('engine', ['graph', 'fused'])
-@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init'])
+@pytest.mark.parametrize('name', ['tiny_init', 'tiny_trained', 'config1_init', 'config2_init', 'config4_init'])
 def test_greedy_decode_matches_reference(name, engine, monkeypatch):
     """Both decode engines (CUDA graph of per-op kernels; one persistent cooperative kernel) against the reference's tokens."""
     monkeypatch.setenv('PLANK_B200_DECODE', engine)

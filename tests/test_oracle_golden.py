@@ -73,9 +73,11 @@ def test_pointer_mask_matches_closed_form():
                 assert bool(pm[i, j]) == syn.pointer_allowed(i, j)
 
 
-def test_config2_first_rows():
-    """Full-size model (d=512, 6+6): loss + dists of sample 0 against the reference."""
-    cfg, sd, batch, g = case('config2_init')
+@pytest.mark.parametrize('name', ['config2_init', 'config4_init'])
+def test_full_model_first_rows(name):
+    """Full-size model (d=512, 6+6) at BASELINE configs[1] (S=512, T=256) and configs[3] (train_visible.yaml: S=999, T=128)
+    shapes: loss + dists of sample 0 against the reference."""
+    cfg, sd, batch, g = case(name)
     m = OraclePlankModel(cfg, sd)
     m.training = True
     with torch.no_grad():
