@@ -8,24 +8,30 @@
 
 namespace {
 
-constexpr int kCols = 8, kRows = 16, kThreads = 256;       // 8 warps = 8 row pairs
+constexpr int kCols = 8, kThreads = 256;                   // 8 warps; a warp owns R rows of the CTA's 8 columns
 constexpr int kMaxChunks = 12;                              // K <= 1536
 
+// R = rows per warp (CTA = 8*R rows x 8 columns), NCH = upper bound of K/128 (x chunks kept in registers).
+// R = 2 made every 8 FFMA wait for one LDS.128 of W (the kernel ran at the shared-memory pipe); R = 4 halves that for
+// the K <= 512 projections (all but FFN2), whose 4 x 4 x-chunks still fit in registers.
+template <int R, int NCH>
 __global__ void __launch_bounds__(kThreads) gemm_skinny_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw,
                                                                  const float* __restrict__ bias, float* __restrict__ c, int64_t ldc, int M, int N,
                                                                  int K, int relu) {
   extern __shared__ __align__(16) float ws[];               // [kCols][K]
   const int n0 = blockIdx.x * kCols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r0 = blockIdx.y * kRows + warp * 2, r1 = r0 + 1;
+  const int r0 = blockIdx.y * (8 * R) + warp * R;
   const int nchunk = K / 128;                                // float4 chunks per lane
   // issue this lane's x loads first: they overlap the W staging below
-  const float* x0 = x + (int64_t)min(r0, M - 1) * ldx + lane * 4;
-  const float* x1 = x + (int64_t)min(r1, M - 1) * ldx + lane * 4;
-  float4 a[kMaxChunks], b[kMaxChunks];
+  float4 a[R][NCH];
 #pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i)
-    if (i < nchunk) { a[i] = __ldg(reinterpret_cast<const float4*>(x0 + i * 128)); b[i] = __ldg(reinterpret_cast<const float4*>(x1 + i * 128)); }
+  for (int r = 0; r < R; ++r) {
+    const float* xr = x + (int64_t)min(r0 + r, M - 1) * ldx + lane * 4;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      if (i < nchunk) a[r][i] = __ldg(reinterpret_cast<const float4*>(xr + i * 128));
+  }
   for (int i = threadIdx.x * 4; i < kCols * K; i += kThreads * 4) {
     const int col = i / K, k = i - col * K;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -33,30 +39,37 @@ __global__ void __launch_bounds__(kThreads) gemm_skinny_kernel(const float* __re
     *reinterpret_cast<float4*>(ws + i) = v;
   }
   __syncthreads();
-  float acc0[kCols], acc1[kCols];
+  float acc[R][kCols];
 #pragma unroll
-  for (int j = 0; j < kCols; ++j) acc0[j] = acc1[j] = 0.f;
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-  for (int i = 0; i < kMaxChunks; ++i) {
+    for (int j = 0; j < kCols; ++j) acc[r][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
     if (i < nchunk) {
 #pragma unroll
       for (int j = 0; j < kCols; ++j) {
         const float4 wv = *reinterpret_cast<const float4*>(ws + j * K + i * 128 + lane * 4);
-        acc0[j] = fmaf(a[i].x, wv.x, acc0[j]); acc0[j] = fmaf(a[i].y, wv.y, acc0[j]); acc0[j] = fmaf(a[i].z, wv.z, acc0[j]); acc0[j] = fmaf(a[i].w, wv.w, acc0[j]);
-        acc1[j] = fmaf(b[i].x, wv.x, acc1[j]); acc1[j] = fmaf(b[i].y, wv.y, acc1[j]); acc1[j] = fmaf(b[i].z, wv.z, acc1[j]); acc1[j] = fmaf(b[i].w, wv.w, acc1[j]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float t = acc[r][j];
+          t = fmaf(a[r][i].x, wv.x, t); t = fmaf(a[r][i].y, wv.y, t); t = fmaf(a[r][i].z, wv.z, t); t = fmaf(a[r][i].w, wv.w, t);
+          acc[r][j] = t;
+        }
       }
     }
   }
-  // lanes 0..7 end up with row r0's 8 columns, lanes 8..15 with row r1's
+  // lane (r * 8 + j) ends up with row r0 + r, column n0 + j
   float mine = 0.f;
 #pragma unroll
-  for (int j = 0; j < kCols; ++j) {
-    const float s0 = warp_sum(acc0[j]), s1 = warp_sum(acc1[j]);
-    if (lane == j) mine = s0;
-    if (lane == j + 8) mine = s1;
-  }
-  if (lane < 16) {
-    const int col = n0 + (lane & 7), row = lane < 8 ? r0 : r1;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) {
+      const float sv = warp_sum(acc[r][j]);
+      if (lane == r * kCols + j) mine = sv;
+    }
+  if (lane < R * kCols) {
+    const int col = n0 + (lane & 7), row = r0 + (lane >> 3);
     if (col < N && row < M) {
       float v = mine + (bias != nullptr ? __ldg(bias + col) : 0.f);
       if (relu) v = fmaxf(v, 0.f);
@@ -74,11 +87,16 @@ extern "C" int pa_gemm_skinny_f32(const float* x, int64_t ldx, const float* w, i
   const size_t smem = (size_t)kCols * K * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    PA_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 128 * kMaxChunks * 4));
+    PA_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<2, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 128 * kMaxChunks * 4));
     attr_done = true;
   }
-  dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
-  gemm_skinny_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, ldx, w, ldw, bias, c, ldc, M, N, K, relu);
+  if (K <= 512 && M >= 32) {
+    dim3 grid((N + kCols - 1) / kCols, (M + 31) / 32);
+    gemm_skinny_kernel<4, 4><<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, ldx, w, ldw, bias, c, ldc, M, N, K, relu);
+  } else {
+    dim3 grid((N + kCols - 1) / kCols, (M + 15) / 16);
+    gemm_skinny_kernel<2, kMaxChunks><<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, ldx, w, ldw, bias, c, ldc, M, N, K, relu);
+  }
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
