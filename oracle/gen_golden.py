@@ -136,6 +136,29 @@ def run_case(name, cfg, sd, indices, out_dir, decode=True):
           + f'({time.time() - t0:.0f}s)', flush=True)
 
 
+def noise_cases(tiny, sd, out_dir):
+    # held-out + noisy drawings through the trained model (BASELINE config 5 shape), scored with the reference's OWN
+    # matcher exactly as trainer_complete.py:97-104 does (zero-extent filter, plank 0 = bounding box excluded)
+    from third_party.matcher import build_matcher          # the reference's (Apache-2.0) matcher, used as is
+    matcher = build_matcher(tiny.THRESHOLD)
+    ref = build_model(tiny); ref.load_state_dict(sd)
+    for ratio in (0.0, 0.05, 0.10, 0.20):
+        batch = syn.batch_for(tiny, range(100, 108), noise_ratio=ratio)
+        rec = ref_decode_record(ref, batch)
+        ref.eval()
+        with torch.no_grad():
+            out = ref(batch)
+        prf = []
+        for pred, gt in zip(out['predicts'], out['groundtruths']):
+            valid = torch.all(torch.abs(pred[1:, 3:] - pred[1:, :3]) != 0, dim=1)
+            vp = torch.concat((pred[:1], pred[1:][valid]))
+            prf.append([float(x) for x in matcher(vp[1:], gt[1:])])
+        rec['prf'] = np.array(prf, dtype=np.float64)          # [n, 3] precision, recall, F1 per drawing
+        np.savez_compressed(os.path.join(out_dir, f'tiny_trained_noise{int(ratio * 100):02d}.npz'), **rec)
+        print(f'noise {ratio}: decode len {rec["samples"].shape[1]} min margin {rec["margins"].min():.2e}')
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
@@ -144,6 +167,11 @@ def main():
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if args.only == 'noise':
+        tiny = syn.tiny_cfg()
+        sd = {k: torch.from_numpy(v).float() for k, v in np.load(os.path.join(args.out, 'tiny_trained_weights_fp16.npz')).items()}
+        noise_cases(tiny, sd, args.out)
+        return
     if args.only == 'config4_init':
         c4 = syn.config4(dropout=0.0)
         run_case('config4_init', c4, syn.init_state_dict(c4), range(2), args.out)
@@ -158,13 +186,7 @@ def main():
         np.savez_compressed(wpath, **{k: v.numpy() for k, v in sd16.items()})
     sd = {k: torch.from_numpy(v).float() for k, v in np.load(wpath).items()}
     run_case('tiny_trained', tiny, sd, range(10), args.out)
-    # held-out + noisy drawings through the trained model (BASELINE config 5 shape)
-    ref = build_model(tiny); ref.load_state_dict(sd)
-    for ratio in (0.0, 0.05, 0.10, 0.20):
-        batch = syn.batch_for(tiny, range(100, 108), noise_ratio=ratio)
-        rec = ref_decode_record(ref, batch)
-        np.savez_compressed(os.path.join(args.out, f'tiny_trained_noise{int(ratio * 100):02d}.npz'), **rec)
-        print(f'noise {ratio}: decode len {rec["samples"].shape[1]} min margin {rec["margins"].min():.2e}')
+    noise_cases(tiny, sd, args.out)
 
     c1 = syn.config1()
     run_case('config1_init', c1, syn.init_state_dict(c1), range(4), args.out)

@@ -61,3 +61,32 @@ def token_agreement(samples, attach, g, prefix='dec:', margin_floor=1e-4):
     if samples.shape != ref_s.shape and not bad:
         hard.append(('length', samples.shape, ref_s.shape))
     return len(hard) == 0, {'near_tie_flips': bad, 'hard': hard}
+
+
+def plank_prf(pred, gt, threshold=0.5):
+    """Precision / recall / F1 of one drawing as the reference scores it (TEST INFRASTRUCTURE, restated from
+    ref: trainer_complete.py:100-103 -- drop zero-extent predictions, plank 0 (the bounding box) is excluded --,
+    third_party/boxes.py:197-242 -- axis-aligned 3-D IoU, 0 where the boxes do not intersect -- and
+    third_party/matcher.py:28-61 -- Hungarian assignment on cost -1 for IoU > threshold, 100000 otherwise; a matched pair
+    counts when IoU >= threshold; F1 = 2PR / (P + R + 1e-10)).  pred, gt: integer [n, 6] (min xyz, max xyz)."""
+    from scipy.optimize import linear_sum_assignment
+    pred = np.asarray(torch.as_tensor(pred).cpu(), dtype=np.float64).reshape(-1, 6)
+    gt = np.asarray(torch.as_tensor(gt).cpu(), dtype=np.float64).reshape(-1, 6)
+    if len(pred):
+        keep = np.all(np.abs(pred[1:, 3:] - pred[1:, :3]) != 0, axis=1)
+        pred = np.concatenate([pred[:1], pred[1:][keep]])
+    p, g = pred[1:], gt[1:]
+    n_p, n_g = len(p), len(g)
+    if n_p == 0 or n_g == 0:
+        return 0.0, 0.0, 0.0
+    lwh = np.minimum(p[:, None, 3:], g[None, :, 3:]) - np.maximum(p[:, None, :3], g[None, :, :3])
+    inter = np.clip(lwh, 0, None).prod(-1)
+    vol_p, vol_g = (p[:, 3:] - p[:, :3]).prod(-1), (g[:, 3:] - g[:, :3]).prod(-1)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        iou = np.where(inter > 0, inter / (vol_p[:, None] + vol_g[None, :] - inter), 0.0)
+    cost = np.full((n_p, n_g), 100000)
+    cost[iou > threshold] = -1
+    ri, ci = linear_sum_assignment(cost)
+    tp = float((iou[ri, ci] >= threshold).sum())
+    prec, rec = tp / n_p, tp / n_g
+    return prec, rec, prec * rec * 2 / (prec + rec + 1e-10)

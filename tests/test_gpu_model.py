@@ -8,7 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from _util import case, golden, rel_err, token_agreement, trained_tiny_state_dict  # noqa: E402
+from _util import case, golden, plank_prf, rel_err, token_agreement, trained_tiny_state_dict  # noqa: E402
 from plankassembly_b200 import synthetic as syn  # noqa: E402
 
 TOL = 1e-3          # north-star tolerance for logits / loss (relative, fp32)
@@ -107,6 +107,11 @@ def test_noisy_decode_matches_reference(ratio, engine, monkeypatch):
     out = m(to_dev(batch))
     ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='')
     assert ok, info
+    # BASELINE configs[4]: greedy-decode precision / recall / F1 per drawing identical to the reference's (its own decode
+    # scored by its own matcher, recorded in the fixture); scored here with the restated metric of tests/_util.py
+    if 'prf' in g:
+        prf = np.array([plank_prf(p, t, cfg.THRESHOLD) for p, t in zip(out['predicts'], out['groundtruths'])])
+        assert prf.shape == g['prf'].shape and np.allclose(prf, g['prf'], rtol=0, atol=1e-7), (prf, g['prf'])
 
 
 @pytest.mark.parametrize('chains', [1, 2, 4])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import case, golden, rel_err, token_agreement, trained_tiny_state_dict
+from _util import case, golden, plank_prf, rel_err, token_agreement, trained_tiny_state_dict
 from plank_oracle import OraclePlankModel
 from plankassembly_b200 import synthetic as syn
 
@@ -94,3 +94,24 @@ def test_full_model_cached_decode_matches_reference(name):
     out = OraclePlankModel(cfg, sd).eval_step_cached(batch)
     ok, info = token_agreement(out['samples'].numpy(), out['attach'].numpy(), g)
     assert ok, info
+
+
+@pytest.mark.parametrize('ratio', [0, 5, 10, 20])
+def test_noise_sweep_f1_matches_reference_matcher(ratio):
+    """BASELINE configs[4]: per-drawing precision / recall / F1 of the greedy decode on the noisy held-out drawings.
+    The golden numbers come from the reference's own decode scored by the reference's own matcher; here the oracle's
+    decode is scored by the restated metric (tests/_util.plank_prf), which pins both."""
+    cfg = syn.tiny_cfg()
+    g = golden(f'tiny_trained_noise{ratio:02d}')
+    batch = syn.batch_for(cfg, range(100, 108), noise_ratio=ratio / 100)
+    out = OraclePlankModel(cfg, trained_tiny_state_dict()).eval_step_cached(batch)
+    prf = np.array([plank_prf(p, t, cfg.THRESHOLD) for p, t in zip(out['predicts'], out['groundtruths'])])
+    assert prf.shape == g['prf'].shape and np.allclose(prf, g['prf'], rtol=0, atol=1e-7), (prf, g['prf'])
+
+
+def test_restated_matcher_on_handmade_boxes():
+    gt = np.array([[0, 0, 0, 9, 9, 9], [0, 0, 0, 4, 4, 4], [5, 5, 5, 9, 9, 9], [0, 5, 0, 4, 9, 4]])
+    pred = np.array([[0, 0, 0, 9, 9, 9], [0, 0, 0, 4, 4, 4], [5, 5, 5, 9, 9, 8], [1, 1, 1, 1, 3, 3], [6, 0, 0, 9, 2, 2]])
+    # plank 0 excluded; [1,1,1,1,3,3] has zero extent (dropped); exact match; IoU 0.75 match; one false positive; one miss
+    p, r, f = plank_prf(pred, gt, 0.5)
+    assert (p, r) == (2 / 3, 2 / 3) and abs(f - 2 / 3) < 1e-9
