@@ -237,14 +237,20 @@ def _kv_len(kpm):
     tensor-core attention kernels skip whole key tiles beyond it; nothing changes numerically (those keys carry -inf)."""
     if kpm is None:
         return None
-    for t, ver, out in _KV_LEN_CACHE:
-        if t is kpm and ver == kpm._version:
-            return out
+    try:
+        version = kpm._version
+    except RuntimeError:                 # inference tensors do not track versions: no caching
+        version = None
+    if version is not None:
+        for t, ver, out in _KV_LEN_CACHE:
+            if t is kpm and ver == version:
+                return out
     Lk = kpm.shape[1]
     idx = torch.arange(1, Lk + 1, device=kpm.device, dtype=torch.int32)
     out = ((kpm == 0).to(torch.int32) * idx).amax(1).clamp_(min=1).contiguous()
-    _KV_LEN_CACHE.append((kpm, kpm._version, out))
-    del _KV_LEN_CACHE[:-4]
+    if version is not None:
+        _KV_LEN_CACHE.append((kpm, version, out))
+        del _KV_LEN_CACHE[:-4]
     return out
 
 

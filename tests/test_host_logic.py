@@ -18,6 +18,10 @@ def test_kv_len_matches_definition():
     kpm[0, 7] = 0                       # an in-place change bumps the version: recomputed
     assert ops._kv_len(kpm).tolist() == [8, 1, 39, 40, 1]
     assert ops._kv_len(None) is None
+    with torch.inference_mode():        # inference tensors have no version counter: computed, not cached
+        t = torch.zeros(2, 9, dtype=torch.uint8)
+        t[1, 4:] = 1
+        assert ops._kv_len(t).tolist() == [9, 4]
 
 
 def test_zero_pool_learns_demand_and_hands_out_disjoint_zero_views():
