@@ -56,23 +56,26 @@ class GreedyDecoder:
         key = (B, S, str(device), m.vocab_head.weight.data_ptr())
         if self._key == key:
             return
-        d, T, L = m.num_model, m.max_output_length, len(m.decoder.layers)
-        f32 = dict(device=device, dtype=torch.float32)
-        self.cross_kv = [torch.empty(B, S, 2 * d, **f32) for _ in range(L)]
-        self.self_k = [torch.empty(B, T, d, **f32) for _ in range(L)]
-        self.self_v = [torch.empty(B, T, d, **f32) for _ in range(L)]
-        self.hfin = torch.empty(B, T, d, **f32)
-        self.y = torch.empty(B, d, **f32)
-        self.y2 = torch.empty(B, d, **f32)
-        self.o = torch.empty(B, d, **f32)
-        self.kpm = torch.empty(B, S, device=device, dtype=torch.uint8)
-        self.samples = torch.empty(B, T, device=device, dtype=torch.int64)
-        self.attach = torch.empty(B, T, device=device, dtype=torch.int64)
-        self.first_end = torch.empty(B, device=device, dtype=torch.int32)
-        self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)
-        self.state = torch.zeros(16, device=device, dtype=torch.int32)
-        ws = _lib.load().pa_decode_fused_workspace(B, d, m.decoder.layers[0].linear1.weight.shape[0], m.vocab_size)
-        self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
+        # persistent state is allocated as ORDINARY tensors even when the first call happens under torch.inference_mode
+        # (Lightning's test loop): they are reset in place by later calls, which may run outside inference mode
+        with torch.inference_mode(False):
+            d, T, L = m.num_model, m.max_output_length, len(m.decoder.layers)
+            f32 = dict(device=device, dtype=torch.float32)
+            self.cross_kv = [torch.empty(B, S, 2 * d, **f32) for _ in range(L)]
+            self.self_k = [torch.empty(B, T, d, **f32) for _ in range(L)]
+            self.self_v = [torch.empty(B, T, d, **f32) for _ in range(L)]
+            self.hfin = torch.empty(B, T, d, **f32)
+            self.y = torch.empty(B, d, **f32)
+            self.y2 = torch.empty(B, d, **f32)
+            self.o = torch.empty(B, d, **f32)
+            self.kpm = torch.empty(B, S, device=device, dtype=torch.uint8)
+            self.samples = torch.empty(B, T, device=device, dtype=torch.int64)
+            self.attach = torch.empty(B, T, device=device, dtype=torch.int64)
+            self.first_end = torch.empty(B, device=device, dtype=torch.int32)
+            self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)
+            self.state = torch.zeros(16, device=device, dtype=torch.int32)
+            ws = _lib.load().pa_decode_fused_workspace(B, d, m.decoder.layers[0].linear1.weight.shape[0], m.vocab_size)
+            self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
         self._key, self.graph = key, None
 
     def _fused_args(self, B, S):
