@@ -86,3 +86,33 @@ def test_parse_sequence():
     out = m.parse_sequence(seq)
     assert out.shape == (2, 6) and out[1, 5] == 12
     assert m.parse_sequence(torch.tensor([512, 1, 2])).shape == (0, 6)
+
+
+def test_ctypes_struct_layouts_match_header(tmp_path):
+    """The argument structs cross the C ABI by pointer: sizes and the offsets of the trailing fields of the ctypes mirrors
+    must equal what a C compiler sees in include/plank_b200.h."""
+    import ctypes
+    import subprocess
+    from plankassembly_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probes = [('pa_attn_fwd_args', _lib.AttnFwdArgs, ['q', 'ldq', 'B', 'scale', 'seed', 'impl', 'drop_rows', 'kv_len']),
+              ('pa_attn_bwd_args', _lib.AttnBwdArgs, ['q', 'd_o', 'delta', 'lddq', 'kpm', 'scale', 'seed', 'dbias', 'kv_len']),
+              ('pa_gemm_args', _lib.GemmArgs, ['a', 'b', 'c', 'bias', 'seed', 'alpha', 'batch', 'a_batch_rows', 'split_k', 'round_out']),
+              ('pa_decode_layer', _lib.DecodeLayer, ['w_sqkv', 'g1', 'w_f2', 'self_k', 'cross_kv']),
+              ('pa_decode_fused_args', _lib.DecodeFusedArgs, ['B', 'end_token', 'layer_eps', 'layers', 'gf', 'kpm', 'part', 'part_bytes',
+                                                              'hfin', 'first_end', 'state', 'chains', 'profile'])]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "plank_b200.h"', 'int main(void) {']
+    for cname, _, fields in probes:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    seen = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct, fields in probes:
+        assert int(seen[cname]) == ctypes.sizeof(ct), cname
+        for f in fields:
+            assert int(seen[f'{cname}.{f}']) == getattr(ct, f).offset, f'{cname}.{f}'
