@@ -97,9 +97,10 @@ def ref_decode_record(ref, batch):
             'n_predicts': np.array([len(p) for p in out['predicts']])}
 
 
-def train_tiny(cfg, n_samples=10, steps=1500, lr=1e-3):
+def train_tiny(cfg, n_samples=10, steps=1500, lr=1e-3, curve=None):
     """Overfit the reference model on 10 synthetic drawings (BASELINE config-1 recipe) so that
-    decode distributions are peaked and token-exact parity is meaningful."""
+    decode distributions are peaked and token-exact parity is meaningful.
+    curve: optional list that receives (loss, accuracy) of every step (the training-equivalence fixture)."""
     torch.manual_seed(2022)
     ref = build_model(cfg)
     ref.load_state_dict(syn.init_state_dict(cfg))
@@ -112,6 +113,8 @@ def train_tiny(cfg, n_samples=10, steps=1500, lr=1e-3):
         out = ref(batch)
         out['loss'].backward()
         opt.step()
+        if curve is not None:
+            curve.append((out['loss'].item(), float(out['accuracy'])))
         if step % 50 == 0 or step == steps - 1:
             print(f'  train step {step:4d} loss {out["loss"].item():.4f} acc {float(out["accuracy"]):.4f} '
                   f'({time.time() - t0:.0f}s)', flush=True)
@@ -171,6 +174,15 @@ def main():
         tiny = syn.tiny_cfg()
         sd = {k: torch.from_numpy(v).float() for k, v in np.load(os.path.join(args.out, 'tiny_trained_weights_fp16.npz')).items()}
         noise_cases(tiny, sd, args.out)
+        return
+    if args.only == 'curve':
+        # training-equivalence fixture: the reference's own loss/accuracy curve of the tiny overfit recipe
+        # (same seeds, batch, Adam lr 1e-3, dropout 0); the GPU test retrains through the CUDA path and compares
+        curve = []
+        train_tiny(syn.tiny_cfg(), curve=curve)
+        c = np.array(curve, dtype=np.float64)
+        np.savez_compressed(os.path.join(args.out, 'tiny_train_curve.npz'), loss=c[:, 0], accuracy=c[:, 1])
+        print('curve:', len(c), 'steps; first step with accuracy 1.0:', int(np.argmax(c[:, 1] >= 0.9999)))
         return
     if args.only == 'config4_init':
         c4 = syn.config4(dropout=0.0)

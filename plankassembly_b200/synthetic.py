@@ -72,6 +72,10 @@ def config4(dropout=0.2):   # train_visible.yaml shapes, S=999, T=128
     return make_cfg(512, 8, 1024, dropout, 6, 6, 1000, 128, batch_size=64)
 
 
+def fixture_cfg(dropout=0.0):   # full model whose tables cover BOTH configs[1] (S=512,T=256) and configs[3] (S=999,T=128) batches
+    return make_cfg(512, 8, 1024, dropout, 6, 6, 1000, 256, batch_size=64)
+
+
 def tiny_cfg(dropout=0.0):  # small committed-fixture model (tests/golden)
     return make_cfg(128, 4, 256, dropout, 2, 2, 300, 64, batch_size=4)
 
@@ -148,13 +152,18 @@ def _noise(rng, lines, views, types, ratio, length=0.02):
     return lines[keep], views[keep], types[keep]
 
 
-def make_sample(idx, max_input_length, max_output_length, seed=2022, noise_ratio=0.0):
-    """One drawing -> dict of 1-D numpy arrays in LineDataset layout."""
+def make_sample(idx, max_input_length, max_output_length, seed=2022, noise_ratio=0.0, canonical=False):
+    """One drawing -> dict of 1-D numpy arrays in LineDataset layout.
+    canonical=True lists the planks after the bounding box in lexicographic order of their quantised coordinates (a
+    learnable output order, as a curated dataset has; the seeded fixtures of round 1 keep the generation order)."""
     rng = np.random.default_rng(seed + idx)
     S, T = max_input_length - 1, max_output_length
     max_planks = (T - 1) // 6
     n_planks = int(rng.integers(max(2, max_planks // 2), max_planks + 1))
     planks = _make_planks(rng, n_planks)
+    if canonical:
+        qp = quantize(planks[1:])
+        planks = np.concatenate([planks[:1], planks[1:][np.lexsort(qp.T[::-1])]])
 
     lines, views = _plank_lines(planks)
     q = quantize(lines)
@@ -212,9 +221,9 @@ def make_sample(idx, max_input_length, max_output_length, seed=2022, noise_ratio
 
 
 def make_batch(indices, max_input_length, max_output_length, seed=2022, noise_ratio=0.0,
-               device='cpu', with_type=True):
+               device='cpu', with_type=True, canonical=False):
     """Collate samples into the batch dict `PlankModel.forward` consumes."""
-    samples = [make_sample(i, max_input_length, max_output_length, seed, noise_ratio) for i in indices]
+    samples = [make_sample(i, max_input_length, max_output_length, seed, noise_ratio, canonical) for i in indices]
     batch = {'name': [f'synthetic_{i:05d}' for i in indices]}
     for k in samples[0]:
         if k == 'input_type' and not with_type:
@@ -286,3 +295,37 @@ def init_state_dict(cfg, seed=2022, dtype=torch.float32):
 
 
 TOKEN = SimpleNamespace(END=END, PAD=PAD)
+
+
+# ---- compact storage of trained fixture weights: int8 in groups of 32 along the last dim, fp16 scale per group.
+# The fixture's weights ARE the dequantised values: the reference (oracle/gen_golden.py) and the CUDA path both load them.
+Q_GROUP = 32
+
+
+def quantize_state_dict(sd):
+    """-> dict of numpy arrays: '<name>.q' int8 + '<name>.s' fp16 for 2-D tensors with a last dim % 32 == 0, else '<name>' fp32."""
+    out = {}
+    for k, v in sd.items():
+        v = v.detach().float().cpu()
+        if v.dim() == 2 and v.shape[1] % Q_GROUP == 0 and v.numel() >= 4096:
+            g = v.view(v.shape[0], -1, Q_GROUP)
+            s = (g.abs().amax(-1, keepdim=True) / 127.0).clamp_min(1e-12).half()
+            q = torch.round(g / s.float()).clamp_(-127, 127).to(torch.int8)
+            out[k + '.q'], out[k + '.s'] = q.view_as(v).numpy(), s.squeeze(-1).numpy()
+        else:
+            out[k] = v.numpy()
+    return out
+
+
+def dequantize_state_dict(z):
+    """Inverse of quantize_state_dict (z: mapping name -> numpy array, e.g. an open .npz)."""
+    sd = {}
+    for k in z.keys():
+        if k.endswith('.q'):
+            n = k[:-2]
+            q = torch.from_numpy(np.asarray(z[k])).float()
+            s = torch.from_numpy(np.asarray(z[n + '.s'])).float()
+            sd[n] = (q.view(q.shape[0], -1, Q_GROUP) * s.unsqueeze(-1)).view_as(q).contiguous()
+        elif not k.endswith('.s'):
+            sd[k] = torch.from_numpy(np.asarray(z[k])).float()
+    return sd
