@@ -75,6 +75,11 @@ int pa_relu_dropout_bwd_colsum(const float* out, float* g, int64_t rows, int N, 
                                float* dbias, void* stream);
 /* dst = round-to-nearest-TF32(src): shadow copies of the weights for the tensor-core path. */
 int pa_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+/* Error-compensated TF32 operands ("3xTF32", exact-mode inference GEMMs; replaces the cuBLAS fp32 calls torch makes for
+ * models.py:279,293): out[rows, 3K] = [hi | lo | hi] of x[rows, K] (row pitch ldx) for activations (weights = 0) or
+ * [hi | hi | lo] for weights (weights = 1), hi = rn_tf32(x), lo = rn_tf32(x - hi).  One pa_gemm_tf32 over K' = 3K on such
+ * a pair computes hi*hi + lo*hi + hi*lo with FP32 accumulation.  K % 4 == 0, 16-byte aligned pointers. */
+int pa_split3_tf32(const float* x, int64_t ldx, float* out, int64_t rows, int K, int weights, void* stream);
 /* x <- dropout_p(x) in place (sub-block output dropouts are fused into pa_add_ln_*). */
 
 /* ---- K3/K4/K5: multi-head attention core (torch nn/functional.py multi_head_attention_forward

@@ -68,6 +68,7 @@ SIGNATURES = {
     'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, i32, vp]),
     'pa_relu_dropout_bwd_colsum': (i32, [vp, vp, i64, i32, f32, i32, vp, vp]),
     'pa_round_tf32': (i32, [vp, vp, i64, vp]),
+    'pa_split3_tf32': (i32, [vp, i64, vp, i64, i32, i32, vp]),
     'pa_dropout_mask_words': (sz, [i32, i32, i32, i32]),
     'pa_dropout_mask': (i32, [vp, vp, i32, i32, i32, f32, u64, u64, vp]),
     'pa_attn_fwd': (i32, [C.POINTER(AttnFwdArgs), vp]),
@@ -123,20 +124,21 @@ def launch_count():
 
 
 _LAUNCHES = [0]
-PROFILE_HOOK = None     # (entry-point name, list) -> bench.py brackets that kernel with CUDA events
+PROFILE_HOOK = None     # {entry-point name: (list, work_fn | None)} -> bench.py brackets those entry points with CUDA events
 
 
 def call(name, *args, launches=1):
     """Invoke a C-ABI entry point and raise on a non-zero status."""
     lib = load()
     hook = PROFILE_HOOK
-    if hook is not None and hook[0] == name:
+    if hook is not None and name in hook:
         import torch
+        rec, work = hook[name]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        hook[1].append((e0, e1))
+        rec.append((e0, e1, work(args) if work is not None else 0.0))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

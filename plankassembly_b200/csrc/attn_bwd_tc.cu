@@ -824,8 +824,8 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     p.LkPad = (a.Lk + C::BK - 1) / C::BK * C::BK;
     const int smem_q = C::kSmemFixed + 2 * p.LkPad * 4;
     if (smem_q > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_bwd (tc): Lk = %d too long for the dQ kernel's bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
-    static int attr_q = 0;
-    if (smem_q > attr_q) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q)); attr_q = smem_q; }
+    static SmemAttrCache attr_q;
+    if ((rc = pa_set_max_smem(kern, smem_q, attr_q))) return rc;
     p.tiles = (a.Lq + C::BQ - 1) / C::BQ;
     p.items = p.tiles * a.H * a.B;
     kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_q, st>>>(tq, tdo, tk, tkm, tv, p);
@@ -844,8 +844,8 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     p.LqPad = (a.Lq + C::BQ - 1) / C::BQ * C::BQ;
     const int smem_k = C::kSmemFixed + 2 * 2 * p.LqPad * 4;
     if (smem_k > 227 * 1024 || 2 * p.LqPad > 2560) { pa_set_error("pa_attn_bwd (tc): Lq = %d too long for the dK/dV kernel's stat table", a.Lq); return PA_ERR_UNSUPPORTED; }
-    static int attr_k = 0;
-    if (smem_k > attr_k) { PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_k)); attr_k = smem_k; }
+    static SmemAttrCache attr_k;
+    if ((rc = pa_set_max_smem(kern, smem_k, attr_k))) return rc;
     p.tiles = (a.Lk + C::BKV - 1) / C::BKV;
     p.items = p.tiles * a.H * a.B;
     kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_k, st>>>(tk, tv, tq, tqm, tdo, tdom, p);

@@ -474,11 +474,8 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   const int smem_bytes = C::kSmemFixed + 2 * p.LkPad * 4;
   if (smem_bytes > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_fwd (tc): Lk = %d too long for the bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
   auto kern = attn_fwd_tc_kernel<DH>;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+  static SmemAttrCache attr;
+  if (int rc_attr = pa_set_max_smem(kern, smem_bytes, attr)) return rc_attr;
   int grid = p.items < kNumSMs ? p.items : kNumSMs;
   kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
   PA_CHECK_LAUNCH();

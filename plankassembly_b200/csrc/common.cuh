@@ -36,6 +36,29 @@ void pa_set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs (tests on
+// cuda:1, DataParallel) must set it on each of them.  One cache per kernel (a function-local static at the call site).
+#ifdef __cplusplus
+#include <mutex>
+constexpr int kMaxDevices = 32;
+struct SmemAttrCache {
+  std::mutex mu;
+  int bytes[kMaxDevices] = {};
+};
+template <typename Kern>
+inline int pa_set_max_smem(Kern kern, int bytes, SmemAttrCache& cache) {
+  int dev = 0;
+  PA_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(cache.mu);
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (!tracked || bytes > cache.bytes[dev]) {
+    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (tracked) cache.bytes[dev] = bytes;
+  }
+  return PA_OK;
+}
+#endif
+
 // Round-to-nearest conversion to TF32 (10-bit mantissa, low 13 bits zero).  tcgen05 kind::tf32 reads raw
 // fp32 bits and TRUNCATES them, which biases every product by ~2^-11; operands that were rounded here
 // are already exactly representable, so the MMA sees unbiased values.

@@ -85,11 +85,8 @@ extern "C" int pa_gemm_skinny_f32(const float* x, int64_t ldx, const float* w, i
   PA_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 128 == 0 && K <= 128 * kMaxChunks && ldx % 4 == 0 && ldw % 4 == 0);
   PA_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0);
   const size_t smem = (size_t)kCols * K * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    PA_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<2, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCols * 128 * kMaxChunks * 4));
-    attr_done = true;
-  }
+  static SmemAttrCache attr;
+  if (int rc_attr = pa_set_max_smem(gemm_skinny_kernel<2, kMaxChunks>, kCols * 128 * kMaxChunks * 4, attr)) return rc_attr;
   if (K <= 512 && M >= 32) {
     dim3 grid((N + kCols - 1) / kCols, (M + 31) / 32);
     gemm_skinny_kernel<4, 4><<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, ldx, w, ldw, bias, c, ldc, M, N, K, relu);

@@ -59,23 +59,28 @@ struct GemmParams {
   int m_tiles, n_tiles;
 };
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+// TWO = 2-SM UMMA (tcgen05 cta_group::2): a CTA pair works on ONE 256 x BN tile; each CTA stages its 128 rows of A and only
+// HALF of the B tile (BN/2 rows), the tensor cores of the two SMs exchange the halves -- a third less shared-memory traffic
+// per flop than the single-SM form (fp32 operands make these GEMMs smem-bandwidth bound) and room for deeper pipelines.
+template <int BN, bool TWO = false> struct Cfg {
+  static constexpr int kStages = TWO ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6);
   static constexpr int kABytes = BM * BK * 4;           // 16 KB
-  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStageOut = 8 * 32 * 128;        // per epilogue warp: one 32x32 fp32 tile, 128B-swizzled
   static constexpr int kSmem = kStages * kStageBytes + kStageOut + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
+  static_assert(kSmem <= 232448, "dynamic shared memory budget of one CTA");
 };
 
 // CL = 2: CTA pairs (cluster of 2 along M) share every B (weight) tile: each CTA fetches half of it and TMA
 // multicasts the half into both CTAs' smem -> 1/3 less L2->smem traffic per CTA (the K=512 GEMMs are L2-bound).
-template <int BN, bool A_MN, bool B_MN, int CL>
+template <int BN, bool A_MN, bool B_MN, int CL, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-  using C = Cfg<BN>;
+  static_assert(!TWO || CL == 2, "the 2-SM UMMA form runs on CTA pairs");
+  using C = Cfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [8 warps][32 rows][128 B]
@@ -91,11 +96,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
     if (p.tma_store) tc::tma_prefetch_desc(&tma_c);
-    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, CL); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 8); }
+    // TWO: full / tmem_empty are used in the leader (cluster rank 0) only; empty / tmem_full get one multicast commit each
+    for (int s = 0; s < C::kStages; ++s) { tc::mbar_init(full_bar + s, 1); tc::mbar_init(empty_bar + s, TWO ? 1 : CL); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, TWO ? 16 : 8); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (TWO) tc::tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else tc::tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc::tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) tc::cluster_sync();      // the peer's barriers exist before anything is multicast into it
@@ -134,6 +143,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           GTRACE(0, 0);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
+          if constexpr (TWO) {
+            // both CTAs fill their own slot and complete the bytes on the LEADER's full barrier (it expects both halves)
+            const uint32_t lead_full = tc::mapa_u32(tc::smem_u32(full_bar + stage), 0);
+            if (crank == 0) tc::mbar_arrive_expect_tx(full_bar + stage, 2 * C::kStageBytes);
+            if constexpr (!A_MN) {
+              tc::tma_load_2d_pair(sa, &tma_a, kb * BK, b * p.a_batch_rows + mt * BM, lead_full);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 32; ++j) tc::tma_load_2d_pair(sa + j * (BK * 128), &tma_a, mt * BM + j * 32, b * p.a_batch_rows + kb * BK, lead_full);
+            }
+            if constexpr (!B_MN) {
+              tc::tma_load_2d_pair(sb, &tma_b, kb * BK, b * p.b_batch_rows + nt * BN + crank * (BN / 2), lead_full);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tc::tma_load_2d_pair(sb + j * (BK * 128), &tma_b, nt * BN + (crank * (BN / 64) + j) * 32, b * p.b_batch_rows + kb * BK, lead_full);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tc::mbar_arrive_expect_tx(full_bar + stage, C::kStageBytes);
           if constexpr (!A_MN) {
             tc::tma_load_2d(sa, &tma_a, kb * BK, b * p.a_batch_rows + mt * BM, full_bar + stage);
@@ -164,12 +193,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       GTRACE_END(0);
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+  } else if (warp == 1 && (!TWO || crank == 0)) {
+    // ===================================== MMA issuer (TWO: the leader CTA of the pair only) =
     // The whole warp walks the loop (warp-uniform control flow and addresses) and one elected lane issues: inside a
     // divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~70 cycles).
     {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = tc::make_idesc_tf32(TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       GTRACE_DECL(lane == 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -195,22 +224,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int k = 0; k < BK / UK; ++k) {
               const uint64_t dak = tc::desc_advance(da, A_MN ? k * 1024 : k * UK * 4);
               const uint64_t dbk = tc::desc_advance(db, B_MN ? k * 1024 : k * UK * 4);
-              tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if constexpr (TWO) tc::mma_tf32_ss_pair(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc::mma_tf32_ss(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            if constexpr (CL > 1) tc::tc_commit_mcast(empty_bar + stage, 0x3);   // the slot is shared: both CTAs must be done with it
-            else tc::tc_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
-            if (kb + 1 == kb1) tc::tc_commit(tmem_full + acc);                  // accumulator complete -> epilogue
+            if constexpr (TWO) {
+              tc::tc_commit_pair(empty_bar + stage, 0x3);                         // frees the slot in both CTAs
+              if (kb + 1 == kb1) tc::tc_commit_pair(tmem_full + acc, 0x3);        // both halves of the accumulator -> both epilogues
+            } else {
+              if constexpr (CL > 1) tc::tc_commit_mcast(empty_bar + stage, 0x3);   // the slot is shared: both CTAs must be done with it
+              else tc::tc_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
+              if (kb + 1 == kb1) tc::tc_commit(tmem_full + acc);                  // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           GTRACE(1, 2);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        if (kb0 >= kb1) { if (tc::elect_one()) tc::tc_commit(tmem_full + acc); __syncwarp(); }
+        if (kb0 >= kb1) {
+          if (tc::elect_one()) { if constexpr (TWO) tc::tc_commit_pair(tmem_full + acc, 0x3); else tc::tc_commit(tmem_full + acc); }
+          __syncwarp();
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       GTRACE_END(1);
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================================== epilogue =========================================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                  // which of the quarter's two warps: takes chunks half, half+2, ...
@@ -323,7 +361,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        if constexpr (TWO) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(tmem_empty + acc), 0));   // the leader's MMA warp waits for both CTAs
+        else tc::mbar_arrive(tmem_empty + acc);
+      }
       GTRACE(2, 3);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -333,7 +374,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc::tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) tc::cluster_sync();      // do not exit while the peer may still multicast / arrive here
-  if (warp == 1) tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if constexpr (TWO) tc::tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else tc::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,9 +394,9 @@ void resolve_encode() {
     g_encode = (EncodeFn)fn;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL>
+template <int BN, bool A_MN, bool B_MN, int CL, bool TWO = false>
 int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TWO>;
   CUtensorMap ta, tb, tc_map;
   int rc;
   if (!A_MN) rc = pa_make_tmap_2d(&ta, a.a, (uint64_t)a.K, (uint64_t)(a.batch > 1 ? (int64_t)a.batch * a.a_batch_rows : a.M), (uint64_t)a.lda * 4, BK, BM);
@@ -378,12 +422,9 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   } else {
     tc_map = ta;
   }
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_done = true;
-  }
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL, TWO>;
+  static SmemAttrCache attr;
+  if ((rc = pa_set_max_smem(kern, C::kSmem, attr))) return rc;
   int tiles = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.split_k * p.batch;      // cluster steps
   int grid = (tiles * CL < kNumSMs ? tiles * CL : (kNumSMs / CL) * CL);
   if constexpr (CL == 1) {
@@ -403,10 +444,14 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
 
 template <int BN, bool A_MN, bool B_MN>
 int launch(const pa_gemm_args& a, cudaStream_t st) {
-  // CTA pairs pay off once there are enough m tiles to pair up; tiny problems keep the single-CTA kernel
-  static const bool pair_ok = getenv("PLANK_B200_GEMM_PAIR") == nullptr || getenv("PLANK_B200_GEMM_PAIR")[0] != '0';
+  // CTA pairs pay off once there are enough m tiles to pair up; tiny problems keep the single-CTA kernel.
+  // PLANK_B200_GEMM_PAIR: 0 = single CTAs, 1 = pairs sharing B through TMA multicast (cta_group::1 MMAs),
+  // 2 (default) = pairs issuing 2-SM UMMAs (cta_group::2, M = 256)
+  const char* e = getenv("PLANK_B200_GEMM_PAIR");
+  const int mode = e == nullptr ? 2 : atoi(e);
   const int m_tiles = (a.M + BM - 1) / BM;
-  if (pair_ok && m_tiles >= 2 && m_tiles % 2 == 0) return launch_cl<BN, A_MN, B_MN, 2>(a, st);
+  if (mode >= 1 && m_tiles >= 2 && m_tiles % 2 == 0)
+    return mode >= 2 ? launch_cl<BN, A_MN, B_MN, 2, true>(a, st) : launch_cl<BN, A_MN, B_MN, 2, false>(a, st);
   return launch_cl<BN, A_MN, B_MN, 1>(a, st);
 }
 

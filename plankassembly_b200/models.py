@@ -207,6 +207,7 @@ class PlankModel(nn.Module):
         output_value, output_label = batch['output_value'], batch['output_label']
         T = output_value.shape[1]
         tf = self._tf32()
+        ops.begin_step()                                       # derived weight copies are rebuilt once per step
         if torch.is_grad_enabled():
             ops.zero_pool.begin_step(output_value.device)      # one memset for all zero-initialised gradient buffers
 
@@ -238,6 +239,7 @@ class PlankModel(nn.Module):
         """Greedy decoding with persistent K/V caches (same tokens as ref models.py:267-323)."""
         inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
         in_kpm = self._kpm(batch['input_mask'])
+        ops.begin_step()
         x = self._embed_input(inputs)
         memory, _ = self._encode(x, x, in_kpm)
         if self._decoder_engine is None:

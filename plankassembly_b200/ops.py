@@ -367,19 +367,76 @@ def _split_k(tiles, k_blocks):
     return max(1, min(sk, k_blocks // 8 if k_blocks >= 8 else 1))
 
 
-_W_TF32 = {}
+# ---- derived weight copies for the tensor cores.  Both caches hang off the parameter through a WeakKeyDictionary (they
+# die with it) and are refreshed ONCE PER STEP, whatever happened to the weights in between: `begin_step()` (called by
+# PlankModel.train_step / eval_step) opens a new epoch and a copy made in an older epoch is rebuilt on first use.  No
+# reliance on Tensor._version, which updates made through `.data` (EMA swaps, hand-written optimizers) do not bump.
+import weakref
+
+_EPOCH = [0]
+_W_TF32 = weakref.WeakKeyDictionary()      # parameter -> [epoch, rounded copy]           (training GEMMs)
+_W_X3 = weakref.WeakKeyDictionary()        # parameter -> [epoch, [N, 3K] hi|hi|lo copy]  (exact-mode inference GEMMs)
+
+
+def begin_step():
+    _EPOCH[0] += 1
+
+
+def mark_shadow_fresh(W, buf):
+    """An optimizer that writes the rounded copy itself (optim.FusedAdam) registers it for the NEXT step."""
+    _W_TF32[W] = [_EPOCH[0] + 1, buf]
 
 
 def tf32_weight(W):
-    """TF32-rounded shadow copy of a parameter, refreshed when the optimizer has stepped (version bump)."""
-    key = id(W)
-    ent = _W_TF32.get(key)
-    if ent is None or ent[0] != W._version or ent[1].device != W.device or ent[2] is not W:
+    """TF32-rounded shadow copy of a parameter (rebuilt at most once per step)."""
+    ent = _W_TF32.get(W)
+    if ent is None or ent[0] < _EPOCH[0] or ent[1].device != W.device or ent[1].shape != W.shape:
         buf = ent[1] if (ent is not None and ent[1].shape == W.shape and ent[1].device == W.device) else torch.empty_like(W)
         call('pa_round_tf32', W.data_ptr(), buf.data_ptr(), W.numel(), _stream())
-        ent = (W._version, buf, W)
-        _W_TF32[key] = ent
+        ent = [_EPOCH[0], buf]
+        _W_TF32[W] = ent
     return ent[1]
+
+
+def split3(x2, weights=False, out=None):
+    """[rows, K] -> [rows, 3K] error-compensated TF32 operand (csrc/split3.cu)."""
+    rows, K = x2.shape
+    if out is None:
+        out = torch.empty(rows, 3 * K, device=x2.device, dtype=torch.float32)
+    call('pa_split3_tf32', x2.data_ptr(), x2.stride(0), out.data_ptr(), rows, K, int(weights), _stream())
+    return out
+
+
+def x3_weight(W):
+    """[N, 3K] = [hi | hi | lo] copy of a weight for the 3xTF32 GEMMs (rebuilt at most once per step; the buffer itself is
+    stable, so CUDA graphs that captured its address stay valid)."""
+    ent = _W_X3.get(W)
+    if ent is None or ent[0] < _EPOCH[0] or ent[1].device != W.device or ent[1].shape[0] != W.shape[0]:
+        with torch.inference_mode(False):
+            buf = ent[1] if (ent is not None and ent[1].device == W.device and ent[1].shape == (W.shape[0], 3 * W.shape[1])) \
+                else torch.empty(W.shape[0], 3 * W.shape[1], device=W.device, dtype=torch.float32)
+        Wd = W.detach()
+        split3(Wd if Wd.is_contiguous() else Wd.contiguous(), True, buf)
+        ent = [_EPOCH[0], buf]
+        _W_X3[W] = ent
+    return ent[1]
+
+
+def linear_x3(x, W, b, rows=None, relu=False, out=None):
+    """y = x W[rows]^T + b[rows] in fp32-class accuracy on the tensor cores (3xTF32, see csrc/split3.cu).  Inference only."""
+    K = W.shape[1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4:
+        x2 = x2.contiguous()
+    W3 = x3_weight(W)
+    bv = b
+    if rows is not None:
+        W3 = W3[rows]
+        bv = b[rows] if b is not None else None
+    M, N = x2.shape[0], W3.shape[0]
+    y = out if out is not None else torch.empty(M, N, device=x.device, dtype=torch.float32)
+    gemm_tf32(split3(x2), W3, y, M, N, 3 * K, lda=3 * K, ldb=3 * K, ldc=N, bias=bv.detach() if bv is not None else None, relu=relu)
+    return y.view(*x.shape[:-1], N)
 
 
 class Linear(Function):
@@ -487,7 +544,9 @@ GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True):
     """Dense projection y = x W[rows]^T + b[rows].
     tf32=True : our tcgen05 TF32 GEMM (training path; x must be a TF32-rounded tensor).
-    tf32=False: cuBLAS fp32 through torch (exact path used by inference and PLANK_B200_GEMM=cublas)."""
+    tf32=False: fp32-class result.  Without autograd (inference) it is the same tcgen05 kernel fed error-compensated
+                3xTF32 operands (linear_x3); with autograd (the PLANK_B200_GEMM=cublas exact TRAINING path that the
+                parity tests use as a cross-check) cuBLAS fp32 through torch."""
     Wv = W if rows is None else W[rows]
     bv = b if (rows is None or b is None) else b[rows]
     if tf32 and not bias_grad and bv is not None:
@@ -495,6 +554,8 @@ def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=Fal
     if tf32:
         W_r = tf32_weight(W)
         return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx)
+    if GEMM_IMPL == 'tc' and not torch.is_grad_enabled() and p_drop == 0.0 and W.shape[1] % 4 == 0:
+        return linear_x3(x, W, b, rows, relu)        # inference: our own tensor-core kernel in 3xTF32, no cuBLAS
     y = torch.nn.functional.linear(x, Wv, bv)
     if relu:
         y = ReluDropout.apply(y, p_drop)

@@ -23,18 +23,18 @@ def timeit(f, n=10):
     return e0.elapsed_time(e1) / n * 1e3
 from plankassembly_b200 import _lib
 ev = []
-_lib.PROFILE_HOOK = ('pa_attn_fwd', ev)
+_lib.PROFILE_HOOK = {'pa_attn_fwd': (ev, None)}
 for _ in range(10): o = fwd()
 torch.cuda.synchronize()
 _lib.PROFILE_HOOK = None
-t_f = sum(a.elapsed_time(b) for a, b in ev) / len(ev) * 1e3
+t_f = sum(a.elapsed_time(b) for a, b, _ in ev) / len(ev) * 1e3
 ev = []
-_lib.PROFILE_HOOK = ('pa_attn_bwd', ev)
+_lib.PROFILE_HOOK = {'pa_attn_bwd': (ev, None)}
 for _ in range(5):
     o = fwd(); o.backward(w)
 torch.cuda.synchronize()
 _lib.PROFILE_HOOK = None
-t_b = sum(a.elapsed_time(b) for a, b in ev) / len(ev) * 1e3
+t_b = sum(a.elapsed_time(b) for a, b, _ in ev) / len(ev) * 1e3
 fl = 4 * B * H * L * L * dh
 print(f'p_drop={p} debug={os.environ.get("PLANK_B200_ATTN_DEBUG", "0")}: fwd {t_f:7.1f} us ({fl / t_f / 1e6:6.1f} TFLOP/s)   bwd(delta+dq+dkdv) {t_b:7.1f} us ({2.5 * fl / t_b / 1e6:6.1f} TFLOP/s)')
 if int(os.environ.get('PLANK_B200_ATTN_DEBUG', '0')) & 64:

@@ -22,14 +22,14 @@ for mode in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['graph', 'fused']
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         from plankassembly_b200 import _lib
         ev = []
-        _lib.PROFILE_HOOK = ('pa_decode_fused', ev)
+        _lib.PROFILE_HOOK = {'pa_decode_fused': (ev, None)}
         e0.record()
         for _ in range(2):
             o = model(batch)
         e1.record(); torch.cuda.synchronize()
         _lib.PROFILE_HOOK = None
         if ev:
-            print(f'   pa_decode_fused kernel alone: {sum(x.elapsed_time(y) for x, y in ev) / len(ev):.2f} ms')
+            print(f'   pa_decode_fused kernel alone: {sum(x.elapsed_time(y) for x, y, _ in ev) / len(ev):.2f} ms')
     ms = e0.elapsed_time(e1) / 2
     n = o['samples'].numel()
     outs[mode] = o

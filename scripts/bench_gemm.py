@@ -5,7 +5,9 @@ import torch
 from plankassembly_b200 import ops
 shapes = [s for s in [('qkv  fwd', 32768, 1536, 512, {}), ('out  fwd', 32768, 512, 512, {}), ('ffn1 fwd', 32768, 1024, 512, {}), ('ffn2 fwd', 32768, 512, 1024, {}),
           ('qkv  dX ', 32768, 512, 1536, {'b_mn': True}), ('qkv  dW ', 1536, 512, 32768, {'a_mn': True, 'b_mn': True, 'split_k': 6, 'accumulate': True})] if len(sys.argv) < 2 or sys.argv[1] in s[0]]
-for name, M, N, K, kw in shapes:
+modes = os.environ.get('PAIR_MODES', '2,1').split(',')
+for name, M, N, K, kw in [(n + ' pair=' + m, M, N, K, dict(kw, _mode=m)) for (n, M, N, K, kw) in shapes for m in modes]:
+    os.environ['PLANK_B200_GEMM_PAIR'] = kw.pop('_mode')
     if kw.get('a_mn'):
         a = torch.randn(K, M, device='cuda'); lda = M
     else:

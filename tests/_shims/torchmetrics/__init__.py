@@ -9,8 +9,8 @@ class Metric(torch.nn.Module):
 
     def add_state(self, name, default, dist_reduce_fx=None):
         self._defaults[name] = default.clone()
-        setattr(self, name, default.clone())
+        self.register_buffer(name, default.clone(), persistent=False)      # states follow .to(device) like torchmetrics'
 
     def reset(self):
         for k, v in self._defaults.items():
-            setattr(self, k, v.clone())
+            setattr(self, k, v.clone().to(getattr(self, k).device))

@@ -17,5 +17,8 @@ def test_reference_arm_json_line():
     assert d['metric'].startswith('shape-program tokens/sec') and d['value'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
-    assert 'workload' in d['config']
+    staged = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'plankassembly', 'models.py'))
+    assert cb['kind'] == ('reference' if staged else 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert 'cpu' in cb and d['ms_per_step'] > 0 and d['steps'] == 1
+    # same config block as the b200 arm prints (the driver compares them)
+    assert 'BASELINE configs[1]' in d['config']['workload'] and d['config']['global_batch'] == 64

@@ -8,6 +8,14 @@ pytestmark = pytest.mark.gpu
 from _util import rel_err  # noqa: E402
 
 
+@pytest.fixture(autouse=True, params=['2', '1', '0'], ids=['umma2sm', 'multicast', 'single'])
+def pair_mode(request, monkeypatch):
+    """Every case runs in the three CTA organisations of gemm_tc.cu: 2-SM UMMA pairs (cta_group::2, the default), pairs that
+    share B through TMA multicast (cta_group::1), single CTAs."""
+    monkeypatch.setenv('PLANK_B200_GEMM_PAIR', request.param)
+    return request.param
+
+
 def tf32_trunc(x):
     return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
 
@@ -185,3 +193,24 @@ def test_pointer_scores_autograd():
         (out * w.float().cuda()).sum().backward()
         assert rel_err(cpf.grad.cpu(), pf.grad) < 2e-3, (B, T, d)
         assert rel_err(ch.grad.cpu(), h.grad) < 2e-3, (B, T, d)
+
+
+@pytest.mark.parametrize('M,N,K', [(1196, 1536, 512), (64, 514, 512), (4096, 512, 1024), (1000, 1024, 512)])
+def test_linear_x3_is_fp32_class(M, N, K):
+    """3xTF32 (csrc/split3.cu + one pa_gemm_tf32 over K' = 3K): the exact-mode inference projections.  Error against fp64
+    must be at the level of an fp32 GEMM (a plain TF32 GEMM sits at ~5e-4), and no worse than 4x torch's own fp32 matmul."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(M, K, generator=g)
+    w = torch.nn.Parameter(torch.randn(N, K, generator=g) / K ** 0.5)
+    b = torch.randn(N, generator=g)
+    ops.begin_step()
+    with torch.no_grad():
+        y = ops.linear_x3(x.cuda(), w.cuda(), b.cuda(), relu=False)
+        y_rows = ops.linear_x3(x.cuda(), w.cuda(), b.cuda(), rows=slice(N // 2, N))
+        ref32 = torch.nn.functional.linear(x.cuda(), w.detach().cuda(), b.cuda())
+    ref = x.double() @ w.detach().double().T + b.double()
+    e, e32 = rel_err(y.cpu(), ref), rel_err(ref32.cpu(), ref)
+    print(f'x3 {M}x{N}x{K}: rel err vs fp64 {e:.2e} (torch fp32 matmul: {e32:.2e})')
+    assert e < 4e-6 and e < 4 * e32 + 1e-7
+    assert torch.equal(y_rows, y[:, N // 2:])
