@@ -176,6 +176,18 @@ int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const in
 int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
                        float* dists, void* stream);
 
+/* ---- fused Adam over a flat fp32 master buffer that also writes the TF32 shadow weights
+ * (replaces torch.optim.Adam's multi_tensor_apply launches of trainer_complete.py:127-129 plus one pa_round_tf32 per weight).
+ * p, m, v, shadow (may be NULL): flat buffers of the same length; parameter i occupies [param_off[i], param_off[i] +
+ * param_len[i]) (offsets multiples of 4 elements); grads[i]: device pointer of its gradient (NULL = skip, as torch does for
+ * .grad None); the chunk tables split every parameter into pa_adam_chunk_elems()-element pieces: chunk c belongs to parameter
+ * chunk_param[c] and starts at element chunk_off[c] of it.  All tables live in device memory.  step_size = lr / (1 - beta1^t),
+ * inv_bias_correction2_sqrt = 1 / sqrt(1 - beta2^t): torch/optim/adam.py::_single_tensor_adam arithmetic. */
+int pa_adam_chunk_elems(void);
+int pa_adam_flat(float* p, float* m, float* v, float* shadow, const float* const* grads, const int64_t* chunk_off,
+                 const int* chunk_param, const int64_t* param_off, const int64_t* param_len, int n_chunks,
+                 float beta1, float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* stream);
+
 /* Exact-fp32 small-M projection for the decode step: C[M,N] = X[M,K] W[N,K]^T + bias (relu optional).
  * K % 32 == 0 and K <= 1536 (the W slice of a CTA lives in smem). */
 int pa_gemm_skinny_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* c,

@@ -373,9 +373,37 @@ def _split_k(tiles, k_blocks):
 # reliance on Tensor._version, which updates made through `.data` (EMA swaps, hand-written optimizers) do not bump.
 import weakref
 
+
+class _IdWeakCache:
+    """parameter -> entry, keyed by IDENTITY (tensors compare elementwise, so they cannot be WeakKeyDictionary keys) and
+    dropped by a finalizer when the parameter dies, so that neither the parameter nor its copy is pinned in GPU memory."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, t):
+        ent = self.d.get(id(t))
+        return ent[1] if ent is not None and ent[0]() is t else None
+
+    def set(self, t, value):
+        key = id(t)
+        old = self.d.get(key)
+        if old is None or old[0]() is not t:
+            weakref.finalize(t, self._drop, key, weakref.ref(t))
+        self.d[key] = (weakref.ref(t), value)
+
+    def _drop(self, key, ref):
+        ent = self.d.get(key)
+        if ent is not None and ent[0] is ref:
+            del self.d[key]
+
+    def __len__(self):
+        return len(self.d)
+
+
 _EPOCH = [0]
-_W_TF32 = weakref.WeakKeyDictionary()      # parameter -> [epoch, rounded copy]           (training GEMMs)
-_W_X3 = weakref.WeakKeyDictionary()        # parameter -> [epoch, [N, 3K] hi|hi|lo copy]  (exact-mode inference GEMMs)
+_W_TF32 = _IdWeakCache()      # parameter -> [epoch, rounded copy]           (training GEMMs)
+_W_X3 = _IdWeakCache()        # parameter -> [epoch, [N, 3K] hi|hi|lo copy]  (exact-mode inference GEMMs)
 
 
 def begin_step():
@@ -384,7 +412,7 @@ def begin_step():
 
 def mark_shadow_fresh(W, buf):
     """An optimizer that writes the rounded copy itself (optim.FusedAdam) registers it for the NEXT step."""
-    _W_TF32[W] = [_EPOCH[0] + 1, buf]
+    _W_TF32.set(W, [_EPOCH[0] + 1, buf])
 
 
 def tf32_weight(W):
@@ -394,7 +422,7 @@ def tf32_weight(W):
         buf = ent[1] if (ent is not None and ent[1].shape == W.shape and ent[1].device == W.device) else torch.empty_like(W)
         call('pa_round_tf32', W.data_ptr(), buf.data_ptr(), W.numel(), _stream())
         ent = [_EPOCH[0], buf]
-        _W_TF32[W] = ent
+        _W_TF32.set(W, ent)
     return ent[1]
 
 
@@ -418,7 +446,7 @@ def x3_weight(W):
         Wd = W.detach()
         split3(Wd if Wd.is_contiguous() else Wd.contiguous(), True, buf)
         ent = [_EPOCH[0], buf]
-        _W_X3[W] = ent
+        _W_X3.set(W, ent)
     return ent[1]
 
 
