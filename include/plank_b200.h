@@ -176,17 +176,31 @@ int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const in
 int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
                        float* dists, void* stream);
 
+/* ---- batched validation/test post-processing (replaces the per-sample loops of models.py:258-265,309-315,
+ * trainer_complete.py:76-80,97-101 and third_party/boxes.py:197-242; the Hungarian matching stays on the CPU).
+ * pa_parse_sequences: seq [B, n] int64 (row pitch ld) -> planks [B, p_max, dof] int64 = the whole planks before the first
+ *   end_token (0 beyond), n_planks [B] int32 (clipped to p_max), keep [B, p_max] uint8 = plank 0, or all extents
+ *   (coords dof/2.. minus coords 0..) non-zero -- the trainer's zero-extent filter.
+ * pa_plank_iou (dof = 6): for drawing b, rows = the kept predicted planks after plank 0 (in order), columns = ground-truth
+ *   planks 1..n_gt-1; iou [B, p_max-1, g_max-1] fp32 (0 beyond the valid block), bit-identical to pairwise_iou();
+ *   n_rows [B] int32; row_src [B, p_max-1] int32 = source plank index of every row (-1 beyond). */
+int pa_parse_sequences(const int64_t* seq, int64_t ld, int B, int n, int end_token, int dof, int64_t* planks, int p_max,
+                       int* n_planks, uint8_t* keep, void* stream);
+int pa_plank_iou(const int64_t* pred, const uint8_t* keep, const int* n_pred, int p_max, const int64_t* gt, const int* n_gt,
+                 int g_max, int B, float* iou, int* n_rows, int* row_src, void* stream);
+
 /* ---- fused Adam over a flat fp32 master buffer that also writes the TF32 shadow weights
  * (replaces torch.optim.Adam's multi_tensor_apply launches of trainer_complete.py:127-129 plus one pa_round_tf32 per weight).
  * p, m, v, shadow (may be NULL): flat buffers of the same length; parameter i occupies [param_off[i], param_off[i] +
  * param_len[i]) (offsets multiples of 4 elements); grads[i]: device pointer of its gradient (NULL = skip, as torch does for
  * .grad None); the chunk tables split every parameter into pa_adam_chunk_elems()-element pieces: chunk c belongs to parameter
- * chunk_param[c] and starts at element chunk_off[c] of it.  All tables live in device memory.  step_size = lr / (1 - beta1^t),
- * inv_bias_correction2_sqrt = 1 / sqrt(1 - beta2^t): torch/optim/adam.py::_single_tensor_adam arithmetic. */
+ * chunk_param[c] and starts at element chunk_off[c] of it; scalars[2i] = lr / (1 - beta1^t_i), scalars[2i+1] =
+ * 1 / sqrt(1 - beta2^t_i) with t_i the step count of parameter i (torch counts steps per parameter).  All tables live in
+ * device memory.  Arithmetic of torch/optim/adam.py::_single_tensor_adam. */
 int pa_adam_chunk_elems(void);
 int pa_adam_flat(float* p, float* m, float* v, float* shadow, const float* const* grads, const int64_t* chunk_off,
-                 const int* chunk_param, const int64_t* param_off, const int64_t* param_len, int n_chunks,
-                 float beta1, float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* stream);
+                 const int* chunk_param, const int64_t* param_off, const int64_t* param_len, const float* scalars,
+                 int n_chunks, float beta1, float beta2, float eps, void* stream);
 
 /* Exact-fp32 small-M projection for the decode step: C[M,N] = X[M,K] W[N,K]^T + bias (relu optional).
  * K % 32 == 0 and K <= 1536 (the W slice of a CTA lives in smem). */
@@ -202,10 +216,11 @@ int pa_decode_embed(const int64_t* samples, int64_t ld, int B, int t, const int*
                     const float* e_coord, const float* e_pos, int d, float* y, void* stream);
 /* Self-attention for the new position: appends k_new/v_new ([B,ld_new]) at slot t of the caches
  * (cache_len rows of stride ld_cache per sequence) and attends over slots 0..len-1 (len = t+1).
- * Cross-attention: pass k_new = NULL, len = S and kpm ([B,len]). */
+ * Cross-attention: pass k_new = NULL, len = S and kpm ([B,len]); kv_len ([B] int32, may be NULL) = 1 + index of the last
+ * non-PAD key of each sequence: keys beyond it are not streamed at all (exact: they carry -inf). */
 int pa_decode_attn(const float* q, int64_t ldq, const float* k_new, const float* v_new, int64_t ld_new,
                    float* k_cache, float* v_cache, int64_t cache_len, int64_t ld_cache, int t, int len,
-                   const int* t_dev, const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream);
+                   const int* t_dev, const uint8_t* kpm, const int* kv_len, int B, int H, int dh, float scale, float* o, void* stream);
 /* Heads + eval distribution + sampling for step t (models.py:168-186, 235-256).
  * h [B,d] final-normed hidden (also stored into hfin[:,t,:]); lv [B,V]; pf [B,d]; sw [B].
  * Writes samples[b*ld+t], attach[b*ld+t]; first_end[b] = min(first_end[b], t) when the emitted

@@ -124,10 +124,10 @@ def train_tiny(cfg, n_samples=10, steps=1500, lr=1e-3, curve=None):
     return {k: v.detach().half() for k, v in ref.state_dict().items()}
 
 
-def run_case(name, cfg, sd, indices, out_dir, decode=True):
+def run_case(name, cfg, sd, indices, out_dir, decode=True, batch=None):
     ref = build_model(cfg)
     ref.load_state_dict(sd)
-    batch = syn.batch_for(cfg, indices)
+    batch = syn.batch_for(cfg, indices) if batch is None else batch
     t0 = time.time()
     rec = ref_train_record(ref, batch)
     if decode:
@@ -162,6 +162,36 @@ def noise_cases(tiny, sd, out_dir):
 
 
 
+def fixture_cases(out_dir, ratios=(0.0, 0.05, 0.10, 0.20), with_train=True):
+    """Full-size TRAINED fixture: d=512, 6+6 layers, weights = tests/golden/fixture_weights_q8.npz
+    (trained on the B200 through the CUDA path by scripts/train_fixture.py --memorise 32, shipped as int8 groups; the
+    dequantised values are the fixture).  Recorded from the unmodified reference: train step + greedy decode at the
+    configs[1] shape (S=512, T=256) and the configs[3] shape (S=999, T=128), batch 8 each, and the configs[4] noise sweep
+    (the memorised configs[3]-shaped drawings with 0 / 5 / 10 / 20 % of their input lines deleted or shortened), scored with
+    the reference's own matcher."""
+    from third_party.matcher import build_matcher
+    cfg = syn.fixture_cfg(dropout=0.0)
+    sd = syn.dequantize_state_dict(np.load(os.path.join(out_dir, 'fixture_weights_q8.npz')))
+    for name, (mi, mo) in (('fixture_c2', (513, 256)), ('fixture_c4', (1000, 128))) if with_train else ():
+        run_case(name, cfg, sd, range(8), out_dir, batch=syn.make_batch(range(8), mi, mo, canonical=True))
+    matcher = build_matcher(cfg.THRESHOLD)
+    ref = build_model(cfg); ref.load_state_dict(sd)
+    for ratio in ratios:
+        batch = syn.make_batch(range(8), 1000, 128, noise_ratio=ratio, canonical=True)
+        rec = ref_decode_record(ref, batch)
+        ref.eval()
+        with torch.no_grad():
+            out = ref(batch)
+        prf = []
+        for pred, gt in zip(out['predicts'], out['groundtruths']):
+            valid = torch.all(torch.abs(pred[1:, 3:] - pred[1:, :3]) != 0, dim=1)
+            vp = torch.concat((pred[:1], pred[1:][valid]))
+            prf.append([float(x) for x in matcher(vp[1:], gt[1:])])
+        rec['prf'] = np.array(prf, dtype=np.float64)
+        np.savez_compressed(os.path.join(out_dir, f'fixture_noise{int(ratio * 100):02d}.npz'), **rec)
+        print(f'fixture noise {ratio}: decode len {rec["samples"].shape[1]} min margin {rec["margins"].min():.2e} mean P/R/F1 {rec["prf"].mean(0)}', flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
@@ -183,6 +213,12 @@ def main():
         c = np.array(curve, dtype=np.float64)
         np.savez_compressed(os.path.join(args.out, 'tiny_train_curve.npz'), loss=c[:, 0], accuracy=c[:, 1])
         print('curve:', len(c), 'steps; first step with accuracy 1.0:', int(np.argmax(c[:, 1] >= 0.9999)))
+        return
+    if args.only == 'fixture':
+        fixture_cases(args.out)
+        return
+    if args.only == 'fixture_noise_heavy':      # beyond BASELINE's three ratios: where the memorising fixture model starts to fail
+        fixture_cases(args.out, ratios=(0.50, 0.80), with_train=False)
         return
     if args.only == 'config4_init':
         c4 = syn.config4(dropout=0.0)

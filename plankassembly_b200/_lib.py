@@ -78,12 +78,14 @@ SIGNATURES = {
     'pa_dist_loss_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     'pa_dist_loss_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp]),
     'pa_dist_train_full': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
+    'pa_parse_sequences': (i32, [vp, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
+    'pa_plank_iou': (i32, [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]),
     'pa_adam_chunk_elems': (i32, []),
-    'pa_adam_flat': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, vp]),
+    'pa_adam_flat': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, vp]),
     'pa_gemm_skinny_f32': (i32, [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
     'pa_decode_advance': (i32, [vp, vp]),
     'pa_decode_embed': (i32, [vp, i64, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]),
-    'pa_decode_attn': (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i32, i32, vp, vp, i32, i32, i32, f32, vp, vp]),
+    'pa_decode_attn': (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i32, i32, vp, vp, vp, i32, i32, i32, f32, vp, vp]),
     'pa_decode_head': (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i32, vp, vp, i64, vp, vp]),
     'pa_decode_fused_workspace': (sz, [i32, i32, i32, i32]),
     'pa_decode_fused': (i32, [C.POINTER(DecodeFusedArgs), vp]),

@@ -18,11 +18,13 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
                                                         float* __restrict__ shadow, const float* const* __restrict__ grads,
                                                         const int64_t* __restrict__ chunk_off, const int* __restrict__ chunk_param,
                                                         const int64_t* __restrict__ param_off, const int64_t* __restrict__ param_len,
-                                                        int n_chunks, float b1, float b2, float step_size, float inv_bc2_sqrt, float eps) {
+                                                        const float* __restrict__ scalars, int n_chunks, float b1, float b2, float eps) {
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int pi = chunk_param[c];
     const float* g = grads[pi];
     if (g == nullptr) continue;                         // parameter without a gradient this step: untouched, like torch
+    // torch keeps one step count PER PARAMETER (a skipped parameter lags behind): its bias corrections come per parameter
+    const float step_size = scalars[2 * pi], inv_bc2_sqrt = scalars[2 * pi + 1];
     const int64_t base = param_off[pi], start = chunk_off[c];          // start: offset of this chunk inside the parameter
     const int64_t end = min(start + kChunk, param_len[pi]);
     for (int64_t i = start + threadIdx.x * 4; i < end; i += 256 * 4) {
@@ -59,13 +61,13 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
 extern "C" int pa_adam_chunk_elems(void) { return kChunk; }
 
 extern "C" int pa_adam_flat(float* p, float* m, float* v, float* shadow, const float* const* grads, const int64_t* chunk_off,
-                            const int* chunk_param, const int64_t* param_off, const int64_t* param_len, int n_chunks,
-                            float beta1, float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* stream) {
-  PA_CHECK_ARG(p != nullptr && m != nullptr && v != nullptr && grads != nullptr && n_chunks > 0);
+                            const int* chunk_param, const int64_t* param_off, const int64_t* param_len, const float* scalars,
+                            int n_chunks, float beta1, float beta2, float eps, void* stream) {
+  PA_CHECK_ARG(p != nullptr && m != nullptr && v != nullptr && grads != nullptr && scalars != nullptr && n_chunks > 0);
   PA_CHECK_ARG((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow) & 15) == 0);
   const int grid = n_chunks < kNumSMs * 8 ? n_chunks : kNumSMs * 8;
-  adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, m, v, shadow, grads, chunk_off, chunk_param, param_off, param_len, n_chunks,
-                                                            beta1, beta2, step_size, inv_bias_correction2_sqrt, eps);
+  adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, m, v, shadow, grads, chunk_off, chunk_param, param_off, param_len, scalars, n_chunks,
+                                                            beta1, beta2, eps);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

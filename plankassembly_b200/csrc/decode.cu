@@ -12,7 +12,7 @@ template <int DH>
 __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k_new,
                                                                  const float* __restrict__ v_new, int64_t ld_new, float* k_cache,
                                                                  float* v_cache, int64_t cache_len, int64_t ldc, int t_host, int len_host, const int* __restrict__ t_dev,
-                                                                 const uint8_t* __restrict__ kpm, int H, float scale,
+                                                                 const uint8_t* __restrict__ kpm, const int* __restrict__ kv_len, int H, float scale,
                                                                  float* __restrict__ o) {
   extern __shared__ float s_p[];                // [len] scores -> probabilities
   __shared__ float red[kThreads / 32];
@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
   const int d = H * DH;
   // self-attention under a CUDA graph: the step index lives in device memory (len = t + 1)
   const int t = (t_dev != nullptr && k_new != nullptr) ? *t_dev : t_host;
-  const int len = (t_dev != nullptr && k_new != nullptr) ? t + 1 : len_host;
+  // cross-attention over a padded memory: keys beyond kv_len[b] (1 + last non-PAD key) are all PAD (-inf): not even read
+  const int len = (t_dev != nullptr && k_new != nullptr) ? t + 1 : (kv_len != nullptr ? min(len_host, max(kv_len[b], 1)) : len_host);
   float* kc = k_cache + (int64_t)b * cache_len * ldc + h * DH;
   float* vc = v_cache + (int64_t)b * cache_len * ldc + h * DH;
   if (k_new != nullptr) {                       // append this step's key/value (self-attention)
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) decode_attn_kernel(const float* __re
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       if (j < len && sub == 0) {
         float s = a * scale;
-        if (kpm != nullptr && kpm[(int64_t)b * len + j]) s = -INFINITY;
+        if (kpm != nullptr && kpm[(int64_t)b * len_host + j]) s = -INFINITY;
         s_p[j] = s;
         mx = fmaxf(mx, s);
       }
@@ -124,14 +125,14 @@ extern "C" int pa_decode_advance(int* t_dev, void* stream) {
 
 extern "C" int pa_decode_attn(const float* q, int64_t ldq, const float* k_new, const float* v_new, int64_t ld_new,
                               float* k_cache, float* v_cache, int64_t cache_len, int64_t ld_cache, int t, int len,
-                              const int* t_dev, const uint8_t* kpm, int B, int H, int dh, float scale, float* o, void* stream) {
+                              const int* t_dev, const uint8_t* kpm, const int* kv_len, int B, int H, int dh, float scale, float* o, void* stream) {
   PA_CHECK_ARG(ld_cache % 4 == 0 && B > 0 && H > 0 && len > 0 && len <= cache_len && (k_new == nullptr || (t >= 0 && t < cache_len)));
   dim3 grid(H, B);
   size_t smem = (size_t)(t_dev != nullptr ? cache_len : len) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dh) {
-    case 32: decode_attn_kernel<32><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, H, scale, o); break;
-    case 64: decode_attn_kernel<64><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, H, scale, o); break;
+    case 32: decode_attn_kernel<32><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, kv_len, H, scale, o); break;
+    case 64: decode_attn_kernel<64><<<grid, kThreads, smem, st>>>(q, ldq, k_new, v_new, ld_new, k_cache, v_cache, cache_len, ld_cache, t, len, t_dev, kpm, kv_len, H, scale, o); break;
     default: pa_set_error("pa_decode_attn: head dim %d unsupported (32, 64)", dh); return PA_ERR_UNSUPPORTED;
   }
   PA_CHECK_LAUNCH();

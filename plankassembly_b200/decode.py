@@ -27,8 +27,8 @@ import torch.nn.functional as F
 
 import ctypes as C
 
-from . import _lib
-from ._lib import call
+from . import _lib, ops
+from ._lib import GemmArgs, call
 
 
 def _stream():
@@ -46,14 +46,19 @@ class GreedyDecoder:
         if os.environ.get('PLANK_B200_DECODE_GRAPH', '1') != '1':
             self.mode = 'eager'
         self.use_graph = self.mode == 'graph'
+        # sequences decoded together >= this: the step's projections run on the tensor cores as 3xTF32 GEMMs
+        # (csrc/split3.cu + pa_gemm_tf32) instead of the small-M fp32 kernel, which re-stages W for every 32 rows
+        self.tc_min_batch = int(os.environ.get('PLANK_B200_DECODE_TC_MIN', '128'))
         self._key = None
         self.graph = None
         self._lin_out = {}
+        self._x3 = {}
 
     # ------------------------------------------------------------------ persistent state
     def _buffers(self, B, S, device):
         m = self.m
-        key = (B, S, str(device), m.vocab_head.weight.data_ptr())
+        # the captured graph bakes in the address of every parameter it reads: key on all of them
+        key = (B, S, str(device), hash(tuple(p.data_ptr() for p in m.parameters())))
         if self._key == key:
             return
         # persistent state is allocated as ORDINARY tensors even when the first call happens under torch.inference_mode
@@ -69,6 +74,7 @@ class GreedyDecoder:
             self.y2 = torch.empty(B, d, **f32)
             self.o = torch.empty(B, d, **f32)
             self.kpm = torch.empty(B, S, device=device, dtype=torch.uint8)
+            self.kv_len = torch.empty(B, device=device, dtype=torch.int32)
             self.samples = torch.empty(B, T, device=device, dtype=torch.int64)
             self.attach = torch.empty(B, T, device=device, dtype=torch.int64)
             self.first_end = torch.empty(B, device=device, dtype=torch.int32)
@@ -77,6 +83,8 @@ class GreedyDecoder:
             ws = _lib.load().pa_decode_fused_workspace(B, d, m.decoder.layers[0].linear1.weight.shape[0], m.vocab_size)
             self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
         self._key, self.graph = key, None
+        self._lin_out, self._x3 = {}, {}
+        self.tc3 = B >= self.tc_min_batch and ops.GEMM_IMPL == 'tc'
 
     def _fused_args(self, B, S):
         """Argument block of pa_decode_fused (raw device pointers of the canonical fp32 parameters)."""
@@ -118,14 +126,38 @@ class GreedyDecoder:
         a.profile = int(os.environ.get('PLANK_B200_DECODE_PROF', '0'))
         return a, keep
 
-    def _lin(self, x, W, b, key, relu=False):
-        """y = x W^T + b in exact fp32 through pa_gemm_skinny_f32; outputs live in persistent buffers."""
+    def _split(self, x, key):
+        """[M, K] activation -> persistent [M, 3K] hi|lo|hi operand of the 3xTF32 GEMMs (one per distinct input of a step)."""
         M, K = x.shape
-        N = W.shape[0]
+        buf = self._x3.get(key)
+        if buf is None or buf.shape != (M, 3 * K) or buf.device != x.device:
+            with torch.inference_mode(False):
+                buf = self._x3[key] = torch.empty(M, 3 * K, device=x.device, dtype=torch.float32)
+        return ops.split3(x, False, buf)
+
+    def _lin(self, x, W, b, key, relu=False, rows=None, x3=None):
+        """y = x W[rows]^T + b[rows], fp32-class: pa_gemm_skinny_f32 (fp32 FMA) for small batches, the tcgen05 GEMM on
+        3xTF32 operands (x3 = the split of x, shared by the projections that read the same x) for large ones.
+        Outputs live in persistent buffers (CUDA-graph capture)."""
+        M, K = x.shape
+        Wv = W if rows is None else W[rows]
+        bv = b if (rows is None or b is None) else b[rows]
+        N = Wv.shape[0]
         out = self._lin_out.get(key)
         if out is None or out.shape != (M, N) or out.device != x.device:
-            out = self._lin_out[key] = torch.empty(M, N, device=x.device, dtype=torch.float32)
-        call('pa_gemm_skinny_f32', x.data_ptr(), x.stride(0), W.data_ptr(), W.stride(0), b.data_ptr() if b is not None else None,
+            with torch.inference_mode(False):
+                out = self._lin_out[key] = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        if self.tc3 and N >= 64:
+            W3 = ops.x3_weight(W)
+            if rows is not None:
+                W3 = W3[rows]
+            if x3 is None:
+                x3 = self._split(x, key)
+            g = GemmArgs(x3.data_ptr(), 3 * K, 0, W3.data_ptr(), 3 * K, 0, out.data_ptr(), N, bv.data_ptr() if bv is not None else None,
+                         int(relu), 0.0, 0, 0, 1.0, M, N, 3 * K, 1, 0, 0, 0, 1, 0, 0)
+            call('pa_gemm_tf32', C.byref(g), _stream())
+            return out
+        call('pa_gemm_skinny_f32', x.data_ptr(), x.stride(0), Wv.data_ptr(), Wv.stride(0), bv.data_ptr() if bv is not None else None,
              out.data_ptr(), N, M, N, K, int(relu), _stream())
         return out
 
@@ -151,21 +183,22 @@ class GreedyDecoder:
             qkv = self._lin(y, sa.in_proj_weight, sa.in_proj_bias, ('qkv', li))                 # [B,3d]
             base = qkv.data_ptr()
             call('pa_decode_attn', base, 3 * d, base + 4 * d, base + 8 * d, 3 * d, self.self_k[li].data_ptr(),
-                 self.self_v[li].data_ptr(), T, d, t, t + 1, t_dev, None, B, H, dh, scale, self.o.data_ptr(), _stream())
+                 self.self_v[li].data_ptr(), T, d, t, t + 1, t_dev, None, None, B, H, dh, scale, self.o.data_ptr(), _stream())
             a = self._lin(self.o, sa.out_proj.weight, sa.out_proj.bias, ('so', li))
             y, other = self._add_ln(y, a, l.norm1, m.layer_eps, other), y
-            q = self._lin(y, ca.in_proj_weight[:d], ca.in_proj_bias[:d], ('cq', li))
+            q = self._lin(y, ca.in_proj_weight, ca.in_proj_bias, ('cq', li), rows=slice(0, d))
             kvb = self.cross_kv[li].data_ptr()
             call('pa_decode_attn', q.data_ptr(), d, None, None, 0, kvb, kvb + 4 * d, S, 2 * d, 0, S, None, self.kpm.data_ptr(),
-                 B, H, dh, scale, self.o.data_ptr(), _stream())
+                 self.kv_len.data_ptr(), B, H, dh, scale, self.o.data_ptr(), _stream())
             a = self._lin(self.o, ca.out_proj.weight, ca.out_proj.bias, ('co', li))
             y, other = self._add_ln(y, a, l.norm2, m.layer_eps, other), y
             h = self._lin(y, l.linear1.weight, l.linear1.bias, ('f1', li), relu=True)
             f = self._lin(h, l.linear2.weight, l.linear2.bias, ('f2', li))
             y, other = self._add_ln(y, f, l.norm3, m.layer_eps, other), y
         hfin_t = self._add_ln(y, None, m.decoder.norm, 1e-5, other)
-        lv = self._lin(hfin_t, m.vocab_head.weight, m.vocab_head.bias, 'lv')
-        pf = self._lin(hfin_t, m.pointer_head.weight, m.pointer_head.bias, 'pf')
+        h3 = self._split(hfin_t, 'heads') if self.tc3 else None          # one split feeds both head GEMMs
+        lv = self._lin(hfin_t, m.vocab_head.weight, m.vocab_head.bias, 'lv', x3=h3)
+        pf = self._lin(hfin_t, m.pointer_head.weight, m.pointer_head.bias, 'pf', x3=h3)
         sw = self._lin(hfin_t, m.switch_head.weight, m.switch_head.bias, 'sw')
         call('pa_decode_head', hfin_t.data_ptr(), lv.data_ptr(), pf.data_ptr(), sw.data_ptr(), self.hfin.data_ptr(), T, B, d,
              V, t, t_dev, m.token.END, self.samples.data_ptr(), self.attach.data_ptr(), T, self.first_end.data_ptr(), _stream())
@@ -195,10 +228,24 @@ class GreedyDecoder:
         self._buffers(B, S, memory.device)
         # cross-attention K/V: one projection of the encoder memory per layer, kept for all steps
         mem2d = memory.reshape(B * S, d)
+        mem3 = ops.split3(mem2d) if ops.GEMM_IMPL == 'tc' else None      # one 3xTF32 split of the memory feeds all layers
         for li, l in enumerate(m.decoder.layers):
             ca = l.multihead_attn
-            torch.addmm(ca.in_proj_bias[d:], mem2d, ca.in_proj_weight[d:].t(), out=self.cross_kv[li].view(B * S, 2 * d))
+            if mem3 is not None:
+                W3 = ops.x3_weight(ca.in_proj_weight)[d:]
+                ops.gemm_tf32(mem3, W3, self.cross_kv[li], B * S, 2 * d, 3 * d, lda=3 * d, ldb=3 * d, ldc=2 * d, bias=ca.in_proj_bias[d:])
+            else:
+                torch.addmm(ca.in_proj_bias[d:], mem2d, ca.in_proj_weight[d:].t(), out=self.cross_kv[li].view(B * S, 2 * d))
+        del mem3
         self.kpm.copy_(in_kpm)
+        self.kv_len.copy_(ops._kv_len(in_kpm))
+        if self.tc3:                                                     # 3xTF32 weight copies follow the current weights
+            for l in m.decoder.layers:                                   # (pointer-stable buffers: the captured graph stays valid)
+                for W in (l.self_attn.in_proj_weight, l.self_attn.out_proj.weight, l.multihead_attn.in_proj_weight,
+                          l.multihead_attn.out_proj.weight, l.linear1.weight, l.linear2.weight):
+                    ops.x3_weight(W)
+            ops.x3_weight(m.vocab_head.weight)
+            ops.x3_weight(m.pointer_head.weight)
         if self.mode == 'fused':
             args, keep = self._fused_args(B, S)
             call('pa_decode_fused', C.byref(args), _stream())

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, postprocess
 from .decode import GreedyDecoder
 
 
@@ -245,10 +245,11 @@ class PlankModel(nn.Module):
         if self._decoder_engine is None:
             self._decoder_engine = GreedyDecoder(self)
         output, attach = self._decoder_engine.run(memory, in_kpm)
-        predicts, groundtruths = [], []
-        for i in range(output.shape[0]):
-            predicts.append(self.parse_sequence(output[i]))
-            groundtruths.append(self.parse_sequence(batch['output_value'][i]))
+        # ref models.py:309-315 parses every sequence on its own (twice per sample); here one launch per token tensor
+        # (postprocess.py) and the lists are views into the two padded plank tensors
+        dof, END = self.num_output_dof, self.token.END
+        predicts = postprocess.plank_lists(*postprocess.parse_batch(output, END, dof)[:2])
+        groundtruths = postprocess.plank_lists(*postprocess.parse_batch(batch['output_value'], END, dof)[:2])
         return {'samples': output, 'attach': attach, 'predicts': predicts, 'groundtruths': groundtruths}
 
     def forward(self, batch):

@@ -63,6 +63,9 @@ class FusedAdam(torch.optim.Optimizer):
         self._param_len = torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=dev)
         self._gptr_host = torch.zeros(len(ps), dtype=torch.int64).pin_memory()
         self._gptr_dev = torch.zeros(len(ps), dtype=torch.int64, device=dev)
+        self._scal_host = torch.zeros(len(ps), 2, dtype=torch.float32).pin_memory()
+        self._scal_dev = torch.zeros(len(ps), 2, dtype=torch.float32, device=dev)
+        self._steps = [0] * len(ps)
         self._t = 0
         self._keep = None
 
@@ -84,18 +87,20 @@ class FusedAdam(torch.optim.Optimizer):
         if all(x is None for x in grads):
             return loss
         self._t += 1
-        for p, gr in zip(self._ps, grads):
-            if gr is not None:
+        for i, (p, gr) in enumerate(zip(self._ps, grads)):
+            if gr is not None:                                   # torch counts steps per parameter (a skipped one lags behind)
+                self._steps[i] += 1
                 self.state[p]['step'] += 1
+            t = max(self._steps[i], 1)
+            self._scal_host[i, 0] = g['lr'] / (1 - b1 ** t)
+            self._scal_host[i, 1] = 1.0 / math.sqrt(1 - b2 ** t)
         self._gptr_dev.copy_(self._gptr_host, non_blocking=True)
+        self._scal_dev.copy_(self._scal_host, non_blocking=True)
         self._keep = grads                                       # gradients must outlive the launch
-        t = self._t
-        step_size = g['lr'] / (1 - b1 ** t)
-        inv_bc2_sqrt = 1.0 / math.sqrt(1 - b2 ** t)
         call('pa_adam_flat', self.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
              self.shadow.data_ptr() if self.shadow is not None else None, self._gptr_dev.data_ptr(), self._chunk_off.data_ptr(),
-             self._chunk_par.data_ptr(), self._param_off.data_ptr(), self._param_len.data_ptr(), self._n_chunks,
-             b1, b2, step_size, inv_bc2_sqrt, g['eps'], torch.cuda.current_stream().cuda_stream)
+             self._chunk_par.data_ptr(), self._param_off.data_ptr(), self._param_len.data_ptr(), self._scal_dev.data_ptr(),
+             self._n_chunks, b1, b2, g['eps'], torch.cuda.current_stream().cuda_stream)
         if self.shadow is not None:
             for p, o in zip(self._ps, self._offs):
                 if p.dim() == 2:
@@ -118,4 +123,5 @@ class FusedAdam(torch.optim.Optimizer):
                 st['step'] = torch.as_tensor(float(st.get('step', 0.0)), dtype=torch.float32)
                 steps.append(int(st['step']))
                 self.state[p] = st
+        self._steps = steps
         self._t = max(steps) if steps else 0

@@ -17,6 +17,22 @@ CASES = {
 }
 
 
+FIXTURE_SHAPES = {'fixture_c2': (513, 256), 'fixture_c4': (1000, 128)}      # (MAX_INPUT_LENGTH, MAX_OUTPUT_LENGTH) of the batch
+
+
+def fixture_state_dict():
+    """Full-size trained fixture model (scripts/train_fixture.py; int8 groups, the dequantised values ARE the weights)."""
+    return syn.dequantize_state_dict(np.load(os.path.join(GOLDEN, 'fixture_weights_q8.npz')))
+
+
+def fixture_case(name):
+    """-> (cfg, state_dict, batch, golden record) for the trained full-size fixture at the configs[1] / configs[3] shape."""
+    g = golden(name)
+    mi, mo = FIXTURE_SHAPES[name]
+    batch = syn.make_batch([int(i) for i in g['indices']], mi, mo, canonical=True)
+    return syn.fixture_cfg(dropout=0.0), fixture_state_dict(), batch, g
+
+
 def golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
 
@@ -42,14 +58,21 @@ def rel_err(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
-def token_agreement(samples, attach, g, prefix='dec:', margin_floor=1e-4):
-    """Compare greedy tokens with the reference's.  Returns (exact, first_mismatch_info).
-    A mismatch only counts as a failure when the reference's own relative top-1/top-2 margin
-    at the first differing step of that row exceeds `margin_floor`."""
+def token_agreement(samples, attach, g, prefix='dec:', margin_floor=1e-4, strict=False):
+    """Compare greedy tokens with the reference's.  Returns (ok, info); info is None when every token is identical.
+    strict=True (trained fixtures): any difference fails.  Otherwise (seeded-init fixtures, whose distributions are nearly
+    flat) a row may differ from the step on at which the reference's own relative top-1/top-2 margin is below
+    `margin_floor` -- info then says how many rows took that escape, and the callers print it."""
     ref_s, ref_a, marg = g[prefix + 'samples'], g[prefix + 'attach'], g[prefix + 'margins']
     samples, attach = np.asarray(samples), np.asarray(attach)
     if samples.shape == ref_s.shape and (samples == ref_s).all() and (attach == ref_a).all():
         return True, None
+    if strict:
+        n = min(samples.shape[1], ref_s.shape[1])
+        rows = [(b, int(np.nonzero((samples[b, :n] != ref_s[b, :n]) | (attach[b, :n] != ref_a[b, :n]))[0][0]))
+                for b in range(ref_s.shape[0]) if ((samples[b, :n] != ref_s[b, :n]) | (attach[b, :n] != ref_a[b, :n])).any()]
+        return False, {'strict': True, 'shapes': (samples.shape, ref_s.shape),
+                       'first_mismatch (row, step, reference margin)': [(b, t, float(marg[b, t])) for b, t in rows]}
     bad = []
     n = min(samples.shape[1], ref_s.shape[1])
     for b in range(ref_s.shape[0]):
@@ -60,7 +83,7 @@ def token_agreement(samples, attach, g, prefix='dec:', margin_floor=1e-4):
     hard = [x for x in bad if x[2] > margin_floor]
     if samples.shape != ref_s.shape and not bad:
         hard.append(('length', samples.shape, ref_s.shape))
-    return len(hard) == 0, {'near_tie_flips': bad, 'hard': hard}
+    return len(hard) == 0, {'near_tie_flips': bad, 'hard': hard, 'rows_escaped': len(bad) - len([x for x in hard if len(x) == 3 and not isinstance(x[0], str)])}
 
 
 def plank_prf(pred, gt, threshold=0.5):

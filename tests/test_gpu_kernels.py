@@ -268,7 +268,7 @@ def test_decode_attn_matches_oracle():
         o = torch.empty(B, d, device=dev())
         base = cq.data_ptr()
         call('pa_decode_attn', base, 3 * d, base + 4 * d, base + 8 * d, 3 * d, ck.data_ptr(), cv.data_ptr(), Tmax, d, t, t + 1,
-             None, None, B, H, dh, dh ** -0.5, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+             None, None, None, B, H, dh, dh ** -0.5, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
         kc[:, t], vc[:, t] = qkv[:, d:2 * d], qkv[:, 2 * d:]
         assert torch.equal(ck.cpu()[:, t], kc[:, t]) and torch.equal(cv.cpu()[:, t], vc[:, t])
         ref = attn_ref(qkv[:, None, :d].double(), kc[:, :t + 1].double(), vc[:, :t + 1].double(), None, False, H)[:, 0]
@@ -284,9 +284,17 @@ def test_decode_attn_matches_oracle():
     ckv, cq, ckpm = kv.to(dev()), q.to(dev()), kpm.to(dev()).view(torch.uint8)
     o = torch.empty(B, d, device=dev())
     call('pa_decode_attn', cq.data_ptr(), d, None, None, 0, ckv.data_ptr(), ckv.data_ptr() + 4 * d, S, 2 * d, 0, S,
-         None, ckpm.data_ptr(), B, H, dh, dh ** -0.5, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+         None, ckpm.data_ptr(), None, B, H, dh, dh ** -0.5, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
     ref = attn_ref(q[:, None].double(), kv[..., :d].double(), kv[..., d:].double(), kpm, False, H)[:, 0]
     assert rel_err(o.cpu(), ref) < 5e-6
+    # with kv_len (1 + last non-PAD key) the PAD tail is not streamed at all: same result, bit for bit
+    from plankassembly_b200 import ops as _ops
+    kv_len = _ops._kv_len(ckpm)
+    assert kv_len.cpu().tolist() == [200, 17]
+    o2 = torch.empty(B, d, device=dev())
+    call('pa_decode_attn', cq.data_ptr(), d, None, None, 0, ckv.data_ptr(), ckv.data_ptr() + 4 * d, S, 2 * d, 0, S,
+         None, ckpm.data_ptr(), kv_len.data_ptr(), B, H, dh, dh ** -0.5, o2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(o2, o)
 
 
 def test_add_ln_folded_linear_bias(ops):

@@ -8,7 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from _util import case, golden, plank_prf, rel_err, token_agreement, trained_tiny_state_dict  # noqa: E402
+from _util import case, fixture_case, fixture_state_dict, golden, plank_prf, rel_err, token_agreement, trained_tiny_state_dict  # noqa: E402
 from plankassembly_b200 import synthetic as syn  # noqa: E402
 
 TOL = 1e-3          # north-star tolerance for logits / loss (relative, fp32)
@@ -89,11 +89,75 @@ def test_greedy_decode_matches_reference(name, engine, monkeypatch):
     cfg, sd, batch, g = case(name)
     m = build(cfg, sd).eval()
     out = m(to_dev(batch))
-    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g)
+    # trained fixtures (peaked distributions): strictly identical tokens.  Seeded-init fixtures (nearly flat distributions,
+    # reference margins down to 1e-6): identical up to the first near-tie of a row; which branch was taken is printed.
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, strict=name.endswith('trained'))
+    print(f'{name}/{engine}: ' + ('all tokens identical' if info is None else f'near-tie escape taken: {info}'))
     assert ok, info
     if info is None:
         assert [len(p) for p in out['predicts']] == list(g['dec:n_predicts'])
     assert len(out['groundtruths']) == len(out['predicts']) == out['samples'].shape[0]
+
+
+# ------------------------------------------------------------------ full-size TRAINED fixture
+@pytest.mark.parametrize('name', ['fixture_c2', 'fixture_c4'])
+def test_trained_fixture_train_step(name, precision):
+    """d=512, 6+6 layers, trained weights, batch 8 at the configs[1] (S=512, T=256) and configs[3] (S=999, T=128) shapes."""
+    cfg, sd, batch, g = fixture_case(name)
+    m = build(cfg, sd).train()
+    out = m.train_step(to_dev(batch), return_dists=True)
+    # the converged loss is ~0.005: a RELATIVE bar on it amplifies log-prob errors 200x, so the bar is 1e-3 of max(|loss|, 1)
+    # (absolute 1e-3 nats) next to the 1e-3 relative bar on the distributions themselves; both precisions
+    print(f'{name}/{precision}: loss {out["loss"].item():.6f} ref {g["loss"]:.6f}  dists rel err {rel_err(out["dists"][0].cpu(), g["dists0"]):.2e}')
+    assert abs(out['loss'].item() - g['loss']) <= TOL * max(abs(g['loss']), 1.0)
+    assert abs(out['accuracy'].item() - g['accuracy']) < 1e-6
+    assert rel_err(out['dists'][0].cpu(), g['dists0']) < TOL
+    out['loss'].backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    if precision == 'exact':
+        floor = 1e-4 * float(np.sqrt((g['grad_norms'] ** 2).sum()))
+        grads = dict(m.named_parameters())
+        for n, norm in zip(g['grad_names'], g['grad_norms']):
+            assert abs(grads[str(n)].grad.double().norm().item() - norm) <= 1e-3 * norm + floor, n
+
+
+@pytest.mark.parametrize('engine', ['graph', 'fused'])
+@pytest.mark.parametrize('name', ['fixture_c2', 'fixture_c4'])
+def test_trained_fixture_greedy_decode_strictly_identical(name, engine, monkeypatch):
+    """Bit-exact greedy tokens at full model size, batch 8, NO near-tie escape: samples and attach must equal the reference's
+    at every step of every row (the rows keep decoding after their own END until the last row has emitted END)."""
+    monkeypatch.setenv('PLANK_B200_DECODE', engine)
+    cfg, sd, batch, g = fixture_case(name)
+    m = build(cfg, sd).eval()
+    out = m(to_dev(batch))
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, strict=True)
+    print(f'{name}/{engine}: reference min margin {g["dec:margins"].min():.2e}, {g["dec:samples"].shape[1]} steps')
+    assert ok, info
+    assert [len(p) for p in out['predicts']] == list(g['dec:n_predicts'])
+
+
+@pytest.mark.parametrize('engine', ['graph', 'fused'])
+@pytest.mark.parametrize('ratio', [0, 5, 10, 20, 50, 80])          # BASELINE configs[4] names 5/10/20; 50/80 are where F1 drops below 1
+def test_trained_fixture_noise_sweep_f1(ratio, engine, monkeypatch):
+    """BASELINE configs[4] at full model size: noisy-input greedy decode, tokens strictly identical and per-drawing
+    precision / recall / F1 equal to what the reference's own decode + matcher gave (F1 is NOT ~0 here: the fixture model
+    reconstructs its drawings, see the fixture's `prf`)."""
+    monkeypatch.setenv('PLANK_B200_DECODE', engine)
+    g = golden(f'fixture_noise{ratio:02d}')
+    cfg = syn.fixture_cfg(dropout=0.0)
+    batch = syn.make_batch(range(8), 1000, 128, noise_ratio=ratio / 100, canonical=True)
+    m = build(cfg, fixture_state_dict()).eval()
+    out = m(to_dev(batch))
+    # heavy noise puts the model off its training distribution: near-ties appear (reference margins down to 1e-6), so
+    # beyond BASELINE's ratios the usual near-tie rule applies; 0..20 % must be strictly identical
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='', strict=ratio <= 20)
+    assert ok, info
+    if info is not None:
+        pytest.skip(f'near-tie escape taken at noise {ratio} %: {info}')
+    from plankassembly_b200 import postprocess
+    prf = postprocess.batched_prf(out['samples'], to_dev(batch)['output_value'], cfg.TOKEN.END, cfg.THRESHOLD)
+XX
+    assert prf.shape == g['prf'].shape and np.allclose(prf, g['prf'], rtol=0, atol=1e-7), (prf, g['prf'])
 
 
 @pytest.mark.parametrize('engine', ['graph', 'fused'])
@@ -105,7 +169,7 @@ def test_noisy_decode_matches_reference(ratio, engine, monkeypatch):
     batch = syn.batch_for(cfg, range(100, 108), noise_ratio=ratio / 100)
     m = build(cfg, trained_tiny_state_dict()).eval()
     out = m(to_dev(batch))
-    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='')
+    ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='', strict=True)
     assert ok, info
     # BASELINE configs[4]: greedy-decode precision / recall / F1 per drawing identical to the reference's (its own decode
     # scored by its own matcher, recorded in the fixture); scored here with the restated metric of tests/_util.py

@@ -159,8 +159,7 @@ def _ddp_worker(rank, world, port, out):
     batch = to_dev(syn.batch_for(cfg, shard_indices(8, rank, world)), dev)
     for _ in range(2):                                          # second pass: bucket views rebuilt, grads accumulate into them
         ddp.zero_grad()
-        out = ddp(batch)
-        out['loss'].backward()
+        ddp(batch)['loss'].backward()
     torch.cuda.synchronize()
     if rank == 0:
         torch.save({n: p.grad.cpu() for n, p in m.named_parameters()}, out)
