@@ -169,9 +169,12 @@ def run_train(args, rank, world, local_rank):
     model = build_model(cfg)
     model.load_state_dict(syn.init_state_dict(cfg))
     model = model.to(dev).train()
-    # N > 1: every .grad is a view into one flat buffer -> ONE NCCL all-reduce per step (parallel.py)
+    # N > 1: ONE NCCL all-reduce (average) per step over the concatenated gradients (parallel.py)
     reducer = GradAllReduce(model.parameters()) if world > 1 else None
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.LR, fused=True)
+    # Adam as one launch over a flat master buffer that also writes the TF32 shadow weights (optim.py);
+    # --torch-adam times the reference's own optimizer object (torch.optim.Adam, fused) instead
+    from plankassembly_b200.optim import FusedAdam
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LR, fused=True) if args.torch_adam else FusedAdam(model.parameters(), lr=cfg.LR)
 
     # distinct synthetic drawings per rank (weak scaling: per-GPU batch fixed)
     n_host = 4
@@ -294,7 +297,7 @@ def run_train(args, rank, world, local_rank):
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
         'config': workload_config(args.workload, B, S, T, world, {
-            'attention': model.attn_impl,
+            'attention': model.attn_impl, 'optimizer': 'torch.optim.Adam(fused=True)' if args.torch_adam else 'plankassembly_b200.optim.FusedAdam',
             'l2': 'per-step activations (>3 GB) exceed the 126 MB L2; no explicit flush',
             'e2e': 'pinned H2D of every batch + D2H of (loss, accuracy) every step; the host reads step i while step i+1 runs',
             'encoder_tokens_per_step': B * S * world}),
@@ -324,7 +327,7 @@ def run_train(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res['cpu_baseline'] = cpu_baseline_train(args.workload, sample_batch=16, steps=2)     # ~15-25 s of host work
     if rank == 0 and world == 1 and not args.no_torch_cuda:
-        del model, opt
+        del model, opt, step
         torch.cuda.empty_cache()
         res['torch_cuda'] = torch_cuda_arm(args.workload, B, dev, decode=not args.no_decode)
     return res
@@ -557,6 +560,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-torch-cuda', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--torch-adam', action='store_true', help='step with torch.optim.Adam(fused=True) instead of optim.FusedAdam')
     ap.add_argument('--decode-drawings', type=int, default=1000, help='drawings per GPU in the greedy-decode leg (BASELINE configs[2]: 1000)')
     ap.add_argument('--decode-batch', type=int, default=64)
     ap.add_argument('--profile-decode', action='store_true', help='bracket one greedy decode with cudaProfilerStart/Stop and exit')

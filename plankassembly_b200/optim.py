@@ -77,23 +77,27 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         g = self.param_groups[0]
         b1, b2 = g['betas']
-        grads = []
-        for i, p in enumerate(self._ps):
+        grads, ptrs = [], []
+        for p in self._ps:
             gr = p.grad
             if gr is not None and (gr.dtype != torch.float32 or not gr.is_contiguous()):
                 gr = gr.float().contiguous()
             grads.append(gr)
-            self._gptr_host[i] = gr.data_ptr() if gr is not None else 0
+            ptrs.append(gr.data_ptr() if gr is not None else 0)
         if all(x is None for x in grads):
             return loss
         self._t += 1
+        scal, cache = [], {}
         for i, (p, gr) in enumerate(zip(self._ps, grads)):
             if gr is not None:                                   # torch counts steps per parameter (a skipped one lags behind)
                 self._steps[i] += 1
                 self.state[p]['step'] += 1
             t = max(self._steps[i], 1)
-            self._scal_host[i, 0] = g['lr'] / (1 - b1 ** t)
-            self._scal_host[i, 1] = 1.0 / math.sqrt(1 - b2 ** t)
+            if t not in cache:
+                cache[t] = (g['lr'] / (1 - b1 ** t), 1.0 / math.sqrt(1 - b2 ** t))
+            scal.append(cache[t])
+        self._gptr_host.copy_(torch.tensor(ptrs, dtype=torch.int64))
+        self._scal_host.copy_(torch.tensor(scal, dtype=torch.float32))
         self._gptr_dev.copy_(self._gptr_host, non_blocking=True)
         self._scal_dev.copy_(self._scal_host, non_blocking=True)
         self._keep = grads                                       # gradients must outlive the launch

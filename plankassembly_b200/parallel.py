@@ -5,9 +5,14 @@ process per GPU, each rank's loss is the mean over ITS non-PAD targets (ref mode
 averages the gradients over ranks (mean of per-rank means -- not token weighted).  The model is 32 M
 parameters, so there is nothing to shard but the batch and the only exchange is that all-reduce.
 
-`GradAllReduce` keeps every parameter's .grad as a view into ONE flat fp32 buffer, so the exchange is a
-single NCCL all-reduce over NVLink/NVSwitch (~130 MB) instead of DDP's 25 MB buckets; torch DDP also
-works with the module (gradients reach the canonical nn.Parameters) and is what Lightning would use.
+`GradAllReduce` exchanges ALL gradients of a step with ONE NCCL all-reduce (average) over NVLink/NVSwitch (~130 MB):
+after backward the per-parameter gradients (which autograd hands out as fresh tensors -- no pre-existing `.grad`, so no
+AccumulateGrad add kernels) are gathered into one flat buffer by a single concatenation, reduced in place with
+`ReduceOp.AVG` (no separate division), and `.grad` of every parameter becomes a view of that buffer, which the optimizer
+reads in place.  Round 1 kept `.grad` as pre-existing views of a flat buffer instead: autograd then issued one extra add
+kernel per parameter (~270 launches, +1.1 ms per step at N=2 -- most of the round-1 scaling loss) plus a 130 MB `div_`.
+torch DDP also works with the module (gradients reach the canonical nn.Parameters; tests/test_trainer_boundary.py) and is
+what Lightning would use.
 """
 from __future__ import annotations
 
@@ -26,20 +31,28 @@ class GradAllReduce:
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        n = sum(p.numel() for p in self.params)
-        p0 = self.params[0]
-        self.flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.avg = dist.is_initialized() and dist.get_backend(group) == 'nccl'       # gloo has no AVG
+        self.flat = None
 
     def zero_grad(self):
-        """Use instead of optimizer.zero_grad(set_to_none=True): the views must stay attached."""
-        self.flat.zero_()
+        """Same as optimizer.zero_grad(set_to_none=True): autograd then STEALS each gradient instead of adding into it."""
+        for p in self.params:
+            p.grad = None
 
     def sync(self):
         """Average gradients over the ranks (call after backward, before optimizer.step)."""
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self.world)
+        ps = [p for p in self.params if p.grad is not None]
+        if self.world <= 1 or not ps:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])          # one gather kernel, 130 MB
+        if self.avg:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.grad = flat[off:off + n].view_as(p)
+            off += n
+        self.flat = flat

@@ -29,8 +29,8 @@ def _worker(rank, world, port, out):
     idx = shard_indices(8, rank, world)
     red.zero_grad()
     m.train_step(syn.batch_for(cfg, idx))['loss'].backward()
-    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in m.parameters())   # views stayed attached
     red.sync()
+    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in m.parameters())   # gradients are views of the reduced buffer
     if rank == 0:
         torch.save({'flat': red.flat.clone(), 'idx': idx}, out)
     dist.barrier()

@@ -148,7 +148,7 @@ def test_trained_fixture_noise_sweep_f1(ratio, engine, monkeypatch):
     batch = syn.make_batch(range(8), 1000, 128, noise_ratio=ratio / 100, canonical=True)
     m = build(cfg, fixture_state_dict()).eval()
     out = m(to_dev(batch))
-    # heavy noise puts the model off its training distribution: near-ties appear (reference margins down to 1e-6), so
+    # heavy noise puts the model off its training distribution: near-ties appear (reference margins down to 9e-4), so
     # beyond BASELINE's ratios the usual near-tie rule applies; 0..20 % must be strictly identical
     ok, info = token_agreement(out['samples'].cpu().numpy(), out['attach'].cpu().numpy(), g, prefix='', strict=ratio <= 20)
     assert ok, info
@@ -156,7 +156,9 @@ def test_trained_fixture_noise_sweep_f1(ratio, engine, monkeypatch):
         pytest.skip(f'near-tie escape taken at noise {ratio} %: {info}')
     from plankassembly_b200 import postprocess
     prf = postprocess.batched_prf(out['samples'], to_dev(batch)['output_value'], cfg.TOKEN.END, cfg.THRESHOLD)
-XX
+    print(f'noise {ratio} %: mean P/R/F1 ours {prf.mean(0)} reference {g["prf"].mean(0)}')
+    if ratio <= 20:
+        assert g['prf'][:, 2].mean() > 0.5, 'fixture F1 must be meaningfully above zero'
     assert prf.shape == g['prf'].shape and np.allclose(prf, g['prf'], rtol=0, atol=1e-7), (prf, g['prf'])
 
 
