@@ -49,6 +49,10 @@ class GreedyDecoder:
         # sequences decoded together >= this: the step's projections run on the tensor cores as 3xTF32 GEMMs
         # (csrc/split3.cu + pa_gemm_tf32) instead of the small-M fp32 kernel, which re-stages W for every 32 rows
         self.tc_min_batch = int(os.environ.get('PLANK_B200_DECODE_TC_MIN', '128'))
+        # large batches are decoded as independent CHAINS of this many sequences, one CUDA stream (= one parallel branch of
+        # the captured graph) each: a chain's small-M GEMMs occupy 6-24 SMs, so several chains together fill the machine
+        # and one chain's K/V streaming (HBM) overlaps another chain's projections (tensor cores)
+        self.chain_rows = int(os.environ.get('PLANK_B200_DECODE_CHAIN_ROWS', '128'))
         self._key = None
         self.graph = None
         self._lin_out = {}
@@ -84,7 +88,11 @@ class GreedyDecoder:
             self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
         self._key, self.graph = key, None
         self._lin_out, self._x3 = {}, {}
-        self.tc3 = B >= self.tc_min_batch and ops.GEMM_IMPL == 'tc'
+        n_chains = max(1, min(16, B // max(1, self.chain_rows)))
+        per = -(-B // n_chains)
+        self.chains = [(c0, min(B, c0 + per)) for c0 in range(0, B, per)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.chains] if len(self.chains) > 1 else []
+        self.tc3 = per >= self.tc_min_batch and ops.GEMM_IMPL == 'tc'
 
     def _fused_args(self, B, S):
         """Argument block of pa_decode_fused (raw device pointers of the canonical fp32 parameters)."""
@@ -168,42 +176,58 @@ class GreedyDecoder:
 
     # ------------------------------------------------------------------ one step
     def _step(self, t, t_dev):
-        """Issue the kernels of decode step t.  t_dev: device pointer of the step counter (graph mode) or None."""
+        """Issue the kernels of decode step t.  t_dev: device pointer of the step counter (graph mode) or None.
+        Every chain of sequences runs on its own stream (forked from / joined into the current one)."""
+        if len(self.chains) == 1:
+            self._step_rows(0, *self.chains[0], t, t_dev)
+        else:
+            main = torch.cuda.current_stream()
+            for ci, (c0, c1) in enumerate(self.chains):
+                st = self.streams[ci]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    self._step_rows(ci, c0, c1, t, t_dev)
+            for st in self.streams:
+                main.wait_stream(st)
+        if t_dev is not None:
+            call('pa_decode_advance', t_dev, _stream())
+
+    def _step_rows(self, ci, c0, c1, t, t_dev):
+        """Decode step t for the sequences c0..c1-1 (one chain) on the current stream."""
         m = self.m
-        B, d = self.y.shape
+        B, d = c1 - c0, self.y.shape[1]
         S = self.kpm.shape[1]
         H, dh, T, V = m.num_head, d // m.num_head, m.max_output_length, m.vocab_size
         scale = dh ** -0.5
         e_val = m.input_embeddings['input_value'].weight
-        y, other = self.y, self.y2
-        call('pa_decode_embed', self.samples.data_ptr(), T, B, t, t_dev, m.num_output_dof, e_val.data_ptr(),
+        y, other, o = self.y[c0:c1], self.y2[c0:c1], self.o[c0:c1]
+        samples, attach = self.samples[c0:c1], self.attach[c0:c1]
+        call('pa_decode_embed', samples.data_ptr(), T, B, t, t_dev, m.num_output_dof, e_val.data_ptr(),
              m.query_coord_embedding.weight.data_ptr(), m.query_pos_embedding.weight.data_ptr(), d, y.data_ptr(), _stream())
         for li, l in enumerate(m.decoder.layers):
             sa, ca = l.self_attn, l.multihead_attn
-            qkv = self._lin(y, sa.in_proj_weight, sa.in_proj_bias, ('qkv', li))                 # [B,3d]
+            qkv = self._lin(y, sa.in_proj_weight, sa.in_proj_bias, (ci, 'qkv', li))                 # [B,3d]
             base = qkv.data_ptr()
-            call('pa_decode_attn', base, 3 * d, base + 4 * d, base + 8 * d, 3 * d, self.self_k[li].data_ptr(),
-                 self.self_v[li].data_ptr(), T, d, t, t + 1, t_dev, None, None, B, H, dh, scale, self.o.data_ptr(), _stream())
-            a = self._lin(self.o, sa.out_proj.weight, sa.out_proj.bias, ('so', li))
+            call('pa_decode_attn', base, 3 * d, base + 4 * d, base + 8 * d, 3 * d, self.self_k[li][c0:c1].data_ptr(),
+                 self.self_v[li][c0:c1].data_ptr(), T, d, t, t + 1, t_dev, None, None, B, H, dh, scale, o.data_ptr(), _stream())
+            a = self._lin(o, sa.out_proj.weight, sa.out_proj.bias, (ci, 'so', li))
             y, other = self._add_ln(y, a, l.norm1, m.layer_eps, other), y
-            q = self._lin(y, ca.in_proj_weight, ca.in_proj_bias, ('cq', li), rows=slice(0, d))
-            kvb = self.cross_kv[li].data_ptr()
-            call('pa_decode_attn', q.data_ptr(), d, None, None, 0, kvb, kvb + 4 * d, S, 2 * d, 0, S, None, self.kpm.data_ptr(),
-                 self.kv_len.data_ptr(), B, H, dh, scale, self.o.data_ptr(), _stream())
-            a = self._lin(self.o, ca.out_proj.weight, ca.out_proj.bias, ('co', li))
+            q = self._lin(y, ca.in_proj_weight, ca.in_proj_bias, (ci, 'cq', li), rows=slice(0, d))
+            kvb = self.cross_kv[li][c0:c1].data_ptr()
+            call('pa_decode_attn', q.data_ptr(), d, None, None, 0, kvb, kvb + 4 * d, S, 2 * d, 0, S, None, self.kpm[c0:c1].data_ptr(),
+                 self.kv_len[c0:c1].data_ptr(), B, H, dh, scale, o.data_ptr(), _stream())
+            a = self._lin(o, ca.out_proj.weight, ca.out_proj.bias, (ci, 'co', li))
             y, other = self._add_ln(y, a, l.norm2, m.layer_eps, other), y
-            h = self._lin(y, l.linear1.weight, l.linear1.bias, ('f1', li), relu=True)
-            f = self._lin(h, l.linear2.weight, l.linear2.bias, ('f2', li))
+            h = self._lin(y, l.linear1.weight, l.linear1.bias, (ci, 'f1', li), relu=True)
+            f = self._lin(h, l.linear2.weight, l.linear2.bias, (ci, 'f2', li))
             y, other = self._add_ln(y, f, l.norm3, m.layer_eps, other), y
         hfin_t = self._add_ln(y, None, m.decoder.norm, 1e-5, other)
-        h3 = self._split(hfin_t, 'heads') if self.tc3 else None          # one split feeds both head GEMMs
-        lv = self._lin(hfin_t, m.vocab_head.weight, m.vocab_head.bias, 'lv', x3=h3)
-        pf = self._lin(hfin_t, m.pointer_head.weight, m.pointer_head.bias, 'pf', x3=h3)
-        sw = self._lin(hfin_t, m.switch_head.weight, m.switch_head.bias, 'sw')
-        call('pa_decode_head', hfin_t.data_ptr(), lv.data_ptr(), pf.data_ptr(), sw.data_ptr(), self.hfin.data_ptr(), T, B, d,
-             V, t, t_dev, m.token.END, self.samples.data_ptr(), self.attach.data_ptr(), T, self.first_end.data_ptr(), _stream())
-        if t_dev is not None:
-            call('pa_decode_advance', t_dev, _stream())
+        h3 = self._split(hfin_t, (ci, 'heads')) if self.tc3 else None          # one split feeds both head GEMMs
+        lv = self._lin(hfin_t, m.vocab_head.weight, m.vocab_head.bias, (ci, 'lv'), x3=h3)
+        pf = self._lin(hfin_t, m.pointer_head.weight, m.pointer_head.bias, (ci, 'pf'), x3=h3)
+        sw = self._lin(hfin_t, m.switch_head.weight, m.switch_head.bias, (ci, 'sw'))
+        call('pa_decode_head', hfin_t.data_ptr(), lv.data_ptr(), pf.data_ptr(), sw.data_ptr(), self.hfin[c0:c1].data_ptr(), T, B, d,
+             V, t, t_dev, m.token.END, samples.data_ptr(), attach.data_ptr(), T, self.first_end[c0:c1].data_ptr(), _stream())
 
     def _capture(self):
         """Warm up (cuBLAS workspaces, kernel attributes) on a side stream, then capture one step."""
