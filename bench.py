@@ -562,7 +562,7 @@ def main():
     ap.add_argument('--no-decode', action='store_true')
     ap.add_argument('--torch-adam', action='store_true', help='step with torch.optim.Adam(fused=True) instead of optim.FusedAdam')
     ap.add_argument('--decode-drawings', type=int, default=1000, help='drawings per GPU in the greedy-decode leg (BASELINE configs[2]: 1000)')
-    ap.add_argument('--decode-batch', type=int, default=64)
+    ap.add_argument('--decode-batch', type=int, default=1024, help='sequences decoded together per GPU (chains of 128 on parallel graph branches)')
     ap.add_argument('--profile-decode', action='store_true', help='bracket one greedy decode with cudaProfilerStart/Stop and exit')
     ap.add_argument('--profile-step', action='store_true', help='bracket ONE step with cudaProfilerStart/Stop (for ncu --profile-from-start off) and exit')
     args = ap.parse_args()

@@ -211,6 +211,11 @@ class PlankModel(nn.Module):
         if torch.is_grad_enabled():
             ops.zero_pool.begin_step(output_value.device)      # one memset for all zero-initialised gradient buffers
 
+        if tf and self._p() > 0 and self._impl() == 1:
+            # all attention-dropout bit planes of this step, generated on a side stream in the shadow of the main stream
+            B, S, H = output_value.shape[0], batch['input_mask'].shape[1], self.num_head
+            ops.MASKS.plan([(B, H, S, S)] * len(self.encoder.layers) + [(B, H, T, T), (B, H, T, S)] * len(self.decoder.layers),
+                           self._p(), output_value.device)
         if tf:
             x, x_r = self._embed_input(inputs, True)
             y, y_r = self._embed_output(output_value, T, True)

@@ -34,6 +34,18 @@ for mode in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['graph', 'fused']
     n = o['samples'].numel()
     outs[mode] = o
     print(f'{mode:6s} B={B}: {ms:8.2f} ms per decode, {o["samples"].shape[1]} steps, {n / ms * 1e3:10.0f} generated tok/s, {ms / o["samples"].shape[1] * 1e3:7.1f} us/step')
+# prefill (encoder + cross-K/V projection) vs the token loop
+with torch.no_grad():
+    from plankassembly_b200 import ops
+    def ev():
+        e = torch.cuda.Event(enable_timing=True); e.record(); return e
+    inputs = {k: v for k, v in batch.items() if k[:5] == 'input'}
+    kpm = model._kpm(batch['input_mask'])
+    for _ in range(2):
+        e0 = ev(); ops.begin_step(); x = model._embed_input(inputs); memory, _ = model._encode(x, x, kpm); e1 = ev()
+        model._decoder_engine.run(memory, kpm); e2 = ev()
+    torch.cuda.synchronize()
+    print(f'   encoder prefill {e0.elapsed_time(e1):.1f} ms, cross-K/V projection + token loop {e1.elapsed_time(e2):.1f} ms')
 if len(outs) == 2:
     a, b = list(outs.values())
     print('samples equal:', torch.equal(a['samples'], b['samples']), ' attach equal:', torch.equal(a['attach'], b['attach']))
