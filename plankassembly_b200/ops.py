@@ -235,14 +235,18 @@ class _MaskPrefetch:
     The planes depend on nothing but (seed, offset, shape); `dropout_mask_kernel` is pure ALU work (Philox) with no DRAM
     reads, 1.3 ms per step when it runs alone in front of each attention call.  PlankModel.train_step announces the
     attention calls of the step (`plan`), all planes are launched at once on a second stream and run in the shadow of the
-    tensor-core / HBM-bound kernels of the main stream; each attention call then `take`s its planes (waiting on their event)."""
+    tensor-core / HBM-bound kernels of the main stream; each attention call then `take`s its planes (waiting on their event).
+
+    MEASURED (round 2, profiles/README.md): no gain and a noisier step (22.6-27.7 ms against a steady 22.65 ms) -- every main-
+    stream kernel is a persistent one-CTA-per-SM design, so the Philox CTAs do not find idle issue slots, they take them.
+    Kept as an opt-in experiment (PLANK_B200_MASK_PREFETCH=1), off by default."""
 
     def __init__(self):
         self.stream, self.q = None, []
 
     def plan(self, shapes, p_drop, device):
         self.q = []
-        if os.environ.get('PLANK_B200_MASK_PREFETCH', '1') != '1':
+        if os.environ.get('PLANK_B200_MASK_PREFETCH', '0') != '1':
             return
         if self.stream is None or self.stream.device != device:
             self.stream = torch.cuda.Stream(device=device)

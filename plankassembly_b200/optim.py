@@ -61,9 +61,13 @@ class FusedAdam(torch.optim.Optimizer):
         self._chunk_par = torch.tensor(c_par, dtype=torch.int32, device=dev)
         self._param_off = torch.tensor(offs, dtype=torch.int64, device=dev)
         self._param_len = torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=dev)
-        self._gptr_host = torch.zeros(len(ps), dtype=torch.int64).pin_memory()
+        # per-step tables (gradient pointers, per-parameter bias corrections) travel through a RING of pinned host slots: the
+        # host runs ahead of the GPU, so a slot may only be rewritten once the copy that read it has executed (its event)
+        self._ring = 4
+        self._gptr_host = [torch.zeros(len(ps), dtype=torch.int64).pin_memory() for _ in range(self._ring)]
+        self._scal_host = [torch.zeros(len(ps), 2, dtype=torch.float32).pin_memory() for _ in range(self._ring)]
+        self._slot_ev = [None] * self._ring
         self._gptr_dev = torch.zeros(len(ps), dtype=torch.int64, device=dev)
-        self._scal_host = torch.zeros(len(ps), 2, dtype=torch.float32).pin_memory()
         self._scal_dev = torch.zeros(len(ps), 2, dtype=torch.float32, device=dev)
         self._steps = [0] * len(ps)
         self._t = 0
@@ -96,10 +100,15 @@ class FusedAdam(torch.optim.Optimizer):
             if t not in cache:
                 cache[t] = (g['lr'] / (1 - b1 ** t), 1.0 / math.sqrt(1 - b2 ** t))
             scal.append(cache[t])
-        self._gptr_host.copy_(torch.tensor(ptrs, dtype=torch.int64))
-        self._scal_host.copy_(torch.tensor(scal, dtype=torch.float32))
-        self._gptr_dev.copy_(self._gptr_host, non_blocking=True)
-        self._scal_dev.copy_(self._scal_host, non_blocking=True)
+        slot = self._t % self._ring
+        if self._slot_ev[slot] is not None:
+            self._slot_ev[slot].synchronize()
+        self._gptr_host[slot].copy_(torch.tensor(ptrs, dtype=torch.int64))
+        self._scal_host[slot].copy_(torch.tensor(scal, dtype=torch.float32))
+        self._gptr_dev.copy_(self._gptr_host[slot], non_blocking=True)
+        self._scal_dev.copy_(self._scal_host[slot], non_blocking=True)
+        self._slot_ev[slot] = torch.cuda.Event()
+        self._slot_ev[slot].record()
         self._keep = grads                                       # gradients must outlive the launch
         call('pa_adam_flat', self.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
              self.shadow.data_ptr() if self.shadow is not None else None, self._gptr_dev.data_ptr(), self._chunk_off.data_ptr(),

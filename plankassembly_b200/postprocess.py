@@ -9,6 +9,9 @@ numbers `HungarianMatcher.forward` returns (tests/test_gpu_postprocess.py checks
 """
 from __future__ import annotations
 
+import json
+import os
+
 import numpy as np
 import torch
 
@@ -60,9 +63,13 @@ def batched_iou(pred, pred_keep, n_pred, gt, n_gt):
 def batched_prf(samples, output_value, end_token, threshold=0.5, dof=6):
     """Precision / recall / F1 of every drawing of a batch, as ref trainer_complete.py:97-104 + third_party/matcher.py score
     them: samples = decoded tokens [B, n], output_value = ground-truth tokens [B, T].  -> float64 array [B, 3]."""
-    from scipy.optimize import linear_sum_assignment
     pred, n_pred, keep = parse_batch(samples, end_token, dof)
     gt, n_gt, _ = parse_batch(output_value, end_token, dof)
+    return _prf_from(pred, n_pred, keep, gt, n_gt, threshold)
+
+
+def _prf_from(pred, n_pred, keep, gt, n_gt, threshold):
+    from scipy.optimize import linear_sum_assignment
     iou, n_rows, _ = batched_iou(pred, keep, n_pred, gt, n_gt)
     iou_h, rows_h, ng_h = iou.cpu().numpy(), n_rows.tolist(), n_gt.tolist()           # the one device->host copy
     out = np.zeros((len(rows_h), 3))
@@ -78,3 +85,32 @@ def batched_prf(samples, output_value, end_token, threshold=0.5, dof=6):
         prec, rec = tp / np.float32(nr), tp / np.float32(ng)                          # the reference divides fp32 tensors
         out[b] = (prec, rec, prec * rec * 2 / (prec + rec + np.float32(1e-10)))
     return out
+
+
+def pred_json_records(names, samples, attach, output_value, end_token, threshold=0.5, dof=6):
+    """the per-drawing records `test_step` dumps (ref trainer_complete.py:97-118) for a whole batch, from the
+    batched device-side post-processing: {"prediction", "attach", "groundtruth", "precision", "recall", "fmeasure"} with the
+    zero-extent planks dropped, `attach` cut to the kept prediction's length, metrics as Python floats of the fp32 values.
+    -> list of (name, dict)."""
+    pred, n_pred, keep = parse_batch(samples, end_token, dof)
+    gt, n_gt, _ = parse_batch(output_value, end_token, dof)
+    prf = _prf_from(pred, n_pred, keep, gt, n_gt, threshold)
+    pred_h, keep_h, np_h = pred.cpu().numpy(), keep.cpu().numpy().astype(bool), n_pred.tolist()
+    gt_h, ng_h, att_h = gt.cpu().numpy(), n_gt.tolist(), attach.cpu().numpy()
+    out = []
+    for b, name in enumerate(names):
+        kept = pred_h[b, :np_h[b]][keep_h[b, :np_h[b]]]                               # plank 0 + non-degenerate planks
+        att = att_h[b, :kept.size].reshape(-1, dof)                                   # ref: atta[:len(valid_pred.flatten())]
+        out.append((name, {'prediction': kept.tolist(), 'attach': att.tolist(), 'groundtruth': gt_h[b, :ng_h[b]].tolist(),
+                           'precision': float(prf[b, 0]), 'recall': float(prf[b, 1]), 'fmeasure': float(prf[b, 2])}))
+    return out
+
+
+def write_pred_jsons(log_dir, records):
+    """Byte-compatible with the reference's writer (ref trainer_complete.py:110-118): one `<name>.json` per drawing under
+    `<log_dir>/pred_jsons`, json.dump(indent=4, separators=(', ', ': '))."""
+    d = os.path.join(log_dir, 'pred_jsons')
+    os.makedirs(d, exist_ok=True)
+    for name, rec in records:
+        with open(os.path.join(d, f'{name}.json'), 'w') as f:
+            json.dump(rec, f, indent=4, separators=(', ', ': '))

@@ -118,8 +118,15 @@ def test_trainer_hooks_run_unchanged(trainer_module, tmp_path):
             t.validation_epoch_end(None)
     with torch.inference_mode():
         t.criterion.reset()
+        from plankassembly_b200 import postprocess
+        ours_dir = tmp_path / 'ours'
         for i, batch in enumerate(t.test_dataloader()):
             t.test_step(to_dev(batch, dev), i)
+            # the batched writer produces the same files as the reference's per-sample loop, byte for byte
+            db = to_dev(batch, dev)
+            o = t.model(db)
+            postprocess.write_pred_jsons(str(ours_dir), postprocess.pred_json_records(
+                batch['name'], o['samples'], o['attach'], db['output_value'], t.cfg.TOKEN.END, t.cfg.THRESHOLD))
             with torch.no_grad():
                 ref_out = ref_model(batch)                       # the reference itself, on the host
             ours = t.model(to_dev(batch, dev))
@@ -128,6 +135,8 @@ def test_trainer_hooks_run_unchanged(trainer_module, tmp_path):
     assert t.logged['val/fmeasure'][0] == t.logged['val/fmeasure'][1]
     files = sorted(os.listdir(tmp_path / 'pred_jsons'))
     assert files == [f'synthetic_{i:05d}.json' for i in range(100, 104)]
+    for f in files:
+        assert open(tmp_path / 'pred_jsons' / f, 'rb').read() == open(tmp_path / 'ours' / 'pred_jsons' / f, 'rb').read(), f
     rec = json.load(open(tmp_path / 'pred_jsons' / files[0]))
     assert set(rec) == {'prediction', 'attach', 'groundtruth', 'precision', 'recall', 'fmeasure'}
     t.train()
