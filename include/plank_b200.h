@@ -176,6 +176,21 @@ int pa_dist_loss_bwd(const float* lv, const float* lp, const float* sw, const in
 int pa_dist_train_full(const float* lv, const float* lp, const float* sw, int B, int T, int V, float inv_d,
                        float* dists, void* stream);
 
+/* ---- batched tokeniser with varlen input (replaces LineDataset.prepare_input_sequence /
+ * prepare_output_sequence, plankassembly/datasets/line_data.py:34-83, 85-109, data_utils.py:6-12, per batch instead of per
+ * sample in CPU workers).  lines [n_total, 4] fp64 (x1, y1, x2, y2 in [-1, 1]), views / types [n_total] int64 (types may be
+ * NULL: sideface batches, then `type` may be NULL too), line_off [B+1] int32 = first line of every drawing.  Outputs: the
+ * six planes of the reference's batch dict, [B, S] int64 / uint8 (S = MAX_INPUT_LENGTH - 1), kv_len [B] int32 = 4 n + 1
+ * (the valid length the attention kernels accept), err: 0, or 1 + index of a drawing with more lines than fit.
+ * pa_tokenize_planks: coords [c_total] fp64 + attach [c_total] int64 (-1 = not attached) with coord_off [B+1] ->
+ * output_value / output_label [B, T] int64, output_mask [B, T] uint8, out_len [B] int32 = n + 1. */
+int pa_tokenize_lines(const double* lines, const int64_t* views, const int64_t* types, const int* line_off, int B, int S,
+                      int n_bits, int end_token, int pad_token, int64_t* value, int64_t* pos, int64_t* coord, int64_t* view,
+                      int64_t* type, uint8_t* mask, int* kv_len, int* err, void* stream);
+int pa_tokenize_planks(const double* coords, const int64_t* attach, const int* coord_off, int B, int T, int n_bits,
+                       int end_token, int pad_token, int vocab, int64_t* value, int64_t* label, uint8_t* mask, int* out_len,
+                       int* err, void* stream);
+
 /* ---- batched validation/test post-processing (replaces the per-sample loops of models.py:258-265,309-315,
  * trainer_complete.py:76-80,97-101 and third_party/boxes.py:197-242; the Hungarian matching stays on the CPU).
  * pa_parse_sequences: seq [B, n] int64 (row pitch ld) -> planks [B, p_max, dof] int64 = the whole planks before the first

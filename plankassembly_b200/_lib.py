@@ -78,6 +78,8 @@ SIGNATURES = {
     'pa_dist_loss_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
     'pa_dist_loss_bwd': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp]),
     'pa_dist_train_full': (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp]),
+    'pa_tokenize_lines': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'pa_tokenize_planks': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     'pa_parse_sequences': (i32, [vp, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
     'pa_plank_iou': (i32, [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]),
     'pa_adam_chunk_elems': (i32, []),
