@@ -56,6 +56,7 @@ struct GemmParams {
   int round_out;
   int debug;              // bit 0: skip the epilogue body (mainloop-only timing experiments)
   int tma_store;          // epilogue stores through smem + TMA (needs a 16-byte row pitch)
+  int epi_direct;         // ... or through the same swizzled smem tile and coalesced st.global.v4 (no TMA queue, no async-proxy fence)
   int m_tiles, n_tiles;
 };
 
@@ -287,8 +288,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (p.tma_store) {
           if (kb1 > kb0 && col0 < p.N) {        // warp-uniform
             uint8_t* my_stage = out_stage + (warp - 2) * (32 * 128);
+            const bool direct = p.epi_direct && !p.accumulate;
             // (two alternating slots per warp were tried: the ~2700-cycle wait moves into the TMA queue, no gain)
-            if (lane == 0 && !(p.debug & 2)) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
+            if (!direct && lane == 0 && !(p.debug & 2)) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
             __syncwarp();
             GTRACE(2, 2);
 #pragma unroll
@@ -312,7 +314,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 for (int e = 0; e < 4; ++e) v[e] = tf32_rn(v[e]);
               }
               // 128B swizzle: 16-byte chunk index XOR (row & 7) -- the layout the C tensor map expects
-              *reinterpret_cast<float4*>(my_stage + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+              tc::st_shared_v4(tc::smem_u32(my_stage) + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4), v[0], v[1], v[2], v[3]);
+            }
+            if (direct) {
+              // read the tile back row-wise: 8 lanes cover one 128-byte row segment (conflict-free: a quarter warp = one
+              // swizzled row), 4 rows per instruction -> fully coalesced 16-byte global stores, nothing queued behind the
+              // producer's TMA loads and no async-proxy fence
+              __syncwarp();
+              const int rr = lane >> 3, cc = lane & 7;
+              const int64_t grow0 = (int64_t)b * p.M + mt * BM + q * 32;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rr;
+                const float4 o = tc::ld_shared_v4(tc::smem_u32(my_stage) + r * 128 + ((cc ^ (r & 7)) << 4));
+                const int col = col0 + cc * 4;
+                if (mt * BM + q * 32 + r < p.M && !(p.debug & 2)) {
+                  float* dst = p.c + (grow0 + r) * p.ldc + col;        // batched C is [batch*M, N] here (tma_store precondition)
+                  if (col + 3 < p.N) *reinterpret_cast<float4*>(dst) = o;
+                  else {
+                    if (col < p.N) dst[0] = o.x;
+                    if (col + 1 < p.N) dst[1] = o.y;
+                    if (col + 2 < p.N) dst[2] = o.z;
+                  }
+                }
+              }
+              continue;
             }
             tc::fence_proxy_async();
             __syncwarp();
@@ -416,6 +442,7 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
   p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
                 (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));
+  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 1 : atoi(e); }
   if (p.tma_store) {
     rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
     if (rc) return rc;

@@ -109,6 +109,17 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// explicit shared-space vector accesses (a pointer derived from the aligned dynamic-smem base loses its address space and
+// compiles to generic ST.E / LD.E)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // One lane of a fully converged warp (the role loops of the MMA warps stay warp-uniform and only the tcgen05.mma /
 // commit instructions are predicated on this: in a divergent `if (lane == 0)` region ptxas wraps every UTCHMMA in
 // an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop, ~70 cycles per MMA).
