@@ -442,7 +442,8 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
   p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
                 (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));
-  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 1 : atoi(e); }
+  // measured (profiles/README.md, round 2): the direct form is SLOWER (QKV projection 120 vs 107 us), so TMA stores stay the default
+  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 0 : atoi(e); }
   if (p.tma_store) {
     rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
     if (rc) return rc;
