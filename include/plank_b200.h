@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 2
+#define PA_ABI_VERSION 3
 #define PA_MAX_TABLES 8
 
 enum pa_status { PA_OK = 0, PA_ERR_ARG = -1, PA_ERR_CUDA = -2, PA_ERR_UNSUPPORTED = -3 };

@@ -114,7 +114,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError => header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.pa_abi_version() != 2:
+    if lib.pa_abi_version() != 3:
         raise PlankB200Error('ABI version mismatch')
     _lib = lib
     return lib

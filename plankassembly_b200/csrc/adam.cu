@@ -65,7 +65,7 @@ extern "C" int pa_adam_flat(float* p, float* m, float* v, float* shadow, const f
                             int n_chunks, float beta1, float beta2, float eps, void* stream) {
   PA_CHECK_ARG(p != nullptr && m != nullptr && v != nullptr && grads != nullptr && scalars != nullptr && n_chunks > 0);
   PA_CHECK_ARG((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)shadow) & 15) == 0);
-  const int grid = n_chunks < kNumSMs * 8 ? n_chunks : kNumSMs * 8;
+  const int grid = n_chunks < pa_num_sms() * 8 ? n_chunks : pa_num_sms() * 8;
   adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, m, v, shadow, grads, chunk_off, chunk_param, param_off, param_len, scalars, n_chunks,
                                                             beta1, beta2, eps);
   PA_CHECK_LAUNCH();

@@ -28,3 +28,15 @@ extern "C" int pa_device_ok(void) {
   }
   return 1;
 }
+
+// SM count of the current device, cached per device (grids are sized in multiples of it; B200 = 148)
+int pa_num_sms() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kNumSMs;
+  }
+  return cache[dev];
+}

@@ -828,7 +828,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     if ((rc = pa_set_max_smem(kern, smem_q, attr_q))) return rc;
     p.tiles = (a.Lq + C::BQ - 1) / C::BQ;
     p.items = p.tiles * a.H * a.B;
-    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_q, st>>>(tq, tdo, tk, tkm, tv, p);
+    kern<<<p.items < pa_num_sms() ? p.items : pa_num_sms(), kThreads, smem_q, st>>>(tq, tdo, tk, tkm, tv, p);
     PA_CHECK_LAUNCH();
   }
   {
@@ -848,7 +848,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
     if ((rc = pa_set_max_smem(kern, smem_k, attr_k))) return rc;
     p.tiles = (a.Lk + C::BKV - 1) / C::BKV;
     p.items = p.tiles * a.H * a.B;
-    kern<<<p.items < kNumSMs ? p.items : kNumSMs, kThreads, smem_k, st>>>(tk, tv, tq, tqm, tdo, tdom, p);
+    kern<<<p.items < pa_num_sms() ? p.items : pa_num_sms(), kThreads, smem_k, st>>>(tk, tv, tq, tqm, tdo, tdom, p);
     PA_CHECK_LAUNCH();
   }
   return PA_OK;

@@ -476,7 +476,7 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   auto kern = attn_fwd_tc_kernel<DH>;
   static SmemAttrCache attr;
   if (int rc_attr = pa_set_max_smem(kern, smem_bytes, attr)) return rc_attr;
-  int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  int grid = p.items < pa_num_sms() ? p.items : pa_num_sms();
   kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
   PA_CHECK_LAUNCH();
   return PA_OK;

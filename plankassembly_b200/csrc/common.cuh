@@ -34,7 +34,8 @@ void pa_set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (compile-time default; launch code sizes its grids with pa_num_sms())
+int pa_num_sms();             // SM count of the CURRENT device (cached per device; falls back to kNumSMs)
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs (tests on
 // cuda:1, DataParallel) must set it on each of them.  One cache per kernel (a function-local static at the call site).

@@ -454,7 +454,7 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   static SmemAttrCache attr;
   if ((rc = pa_set_max_smem(kern, C::kSmem, attr))) return rc;
   int tiles = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.split_k * p.batch;      // cluster steps
-  int grid = (tiles * CL < kNumSMs ? tiles * CL : (kNumSMs / CL) * CL);
+  int grid = (tiles * CL < pa_num_sms() ? tiles * CL : (pa_num_sms() / CL) * CL);
   if constexpr (CL == 1) {
     kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, tc_map, p);
   } else {

@@ -8,7 +8,7 @@
 #include "common.cuh"
 
 constexpr int kLnWarps = 4;
-constexpr int kLnMaxBlocks = kNumSMs * 4;
+static inline int ln_max_blocks() { return pa_num_sms() * 4; }
 
 // Sub-block output dropout of the residual rows: 16 random bits per element, one Philox4x32-10 call per PAIR of float4
 // chunks of a lane (chunk i uses the low halves of the four words when i is even, the high halves when it is odd).
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __res
 
 static int ln_grid(int64_t rows) {
   int64_t nb = (rows + kLnWarps - 1) / kLnWarps;
-  return (int)(nb < kLnMaxBlocks ? nb : kLnMaxBlocks);
+  return (int)(nb < ln_max_blocks() ? nb : ln_max_blocks());
 }
 
 extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 3 * d * sizeof(float); }
@@ -255,7 +255,7 @@ extern "C" int pa_relu_dropout_fwd(float* z, int64_t n, float p_drop, uint64_t s
   PA_CHECK_ARG(n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f);
   if (n == 0) return PA_OK;
   int64_t n4 = n / 4;
-  int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+  int grid = (int)((n4 + 255) / 256 < pa_num_sms() * 16 ? (n4 + 255) / 256 : pa_num_sms() * 16);
   relu_dropout_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)z, n4, p_drop, seed, offset);
   PA_CHECK_LAUNCH();
   return PA_OK;
@@ -284,7 +284,7 @@ extern "C" int pa_relu_dropout_bwd_colsum(const float* out, float* g, int64_t ro
   if (rows == 0) return PA_OK;
   const int cols4 = N / 4, rpi = 256 / cols4;
   int64_t nb = (rows + rpi - 1) / rpi;
-  int grid = (int)(nb < kNumSMs * 4 ? nb : kNumSMs * 4);
+  int grid = (int)(nb < pa_num_sms() * 4 ? nb : pa_num_sms() * 4);
   relu_dropout_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, rows, cols4,
                                                                           p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, round_tf32, dbias);
   PA_CHECK_LAUNCH();
@@ -295,7 +295,7 @@ extern "C" int pa_relu_dropout_bwd(const float* out, float* g, int64_t n, float 
   PA_CHECK_ARG(n >= 0 && n % 4 == 0 && p_drop >= 0.f && p_drop < 1.f);
   if (n == 0) return PA_OK;
   int64_t n4 = n / 4;
-  int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+  int grid = (int)((n4 + 255) / 256 < pa_num_sms() * 16 ? (n4 + 255) / 256 : pa_num_sms() * 16);
   relu_dropout_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)out, (float4*)g, n4, p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, round_tf32);
   PA_CHECK_LAUNCH();
   return PA_OK;
@@ -315,7 +315,7 @@ extern "C" int pa_round_tf32(const float* src, float* dst, int64_t n, void* stre
   if (n == 0) return PA_OK;
   int64_t n4 = n / 4;
   if (n4 > 0) {
-    int grid = (int)((n4 + 255) / 256 < kNumSMs * 16 ? (n4 + 255) / 256 : kNumSMs * 16);
+    int grid = (int)((n4 + 255) / 256 < pa_num_sms() * 16 ? (n4 + 255) / 256 : pa_num_sms() * 16);
     round_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, n4);
     PA_CHECK_LAUNCH();
   }

@@ -34,7 +34,7 @@ extern "C" int pa_split3_tf32(const float* x, int64_t ldx, float* out, int64_t r
   PA_CHECK_ARG(x != nullptr && out != nullptr && rows > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0);
   PA_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) & 15) == 0);
   const int64_t n4 = rows * (K / 4);
-  const int grid = (int)((n4 + 255) / 256 < kNumSMs * 8 ? (n4 + 255) / 256 : kNumSMs * 8);
+  const int grid = (int)((n4 + 255) / 256 < pa_num_sms() * 8 ? (n4 + 255) / 256 : pa_num_sms() * 8);
   split3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, rows, K, weights ? 1 : 0);
   PA_CHECK_LAUNCH();
   return PA_OK;

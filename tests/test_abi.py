@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/plank_b200.h but not exported'
-    assert lib.pa_abi_version() == 2
+    assert lib.pa_abi_version() == 3
 
 
 def test_ctypes_table_matches_header(lib):
