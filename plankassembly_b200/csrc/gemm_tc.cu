@@ -56,7 +56,8 @@ struct GemmParams {
   int round_out;
   int debug;              // bit 0: skip the epilogue body (mainloop-only timing experiments)
   int tma_store;          // epilogue stores through smem + TMA (needs a 16-byte row pitch)
-  int epi_direct;         // ... or through the same swizzled smem tile and coalesced st.global.v4 (no TMA queue, no async-proxy fence)
+  int epi_direct;         // 1: through the same swizzled smem tile and coalesced st.global.v4 (measured slower); 2: register-direct
+  int wide8;              // C rows are 32-byte aligned: the register-direct epilogue may use 256-bit stores
   int m_tiles, n_tiles;
 };
 
@@ -251,6 +252,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp >= 2) {
     // ===================================== epilogue =========================================
+    const uint32_t bias_u32 = tc::smem_u32(bias_s);
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                  // which of the quarter's two warps: takes chunks half, half+2, ...
     int acc = 0; uint32_t acc_phase = 0;
@@ -300,7 +302,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float x = __uint_as_float(r[j + e]) * p.alpha;
-                if (p.bias != nullptr) x += bias_s[c0 + j + e];
+                if (p.bias != nullptr) x += tc::ld_shared_f32(bias_u32 + 4 * (c0 + j + e));
                 if (p.relu) x = fmaxf(x, 0.f);
                 v[e] = x;
               }
@@ -340,7 +342,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               }
               continue;
             }
-            tc::fence_proxy_async();
+            if (!(p.debug & 16)) tc::fence_proxy_async();      // (debug bit 16: timing experiment without the proxy fence)
             __syncwarp();
             if (lane == 0 && !(p.debug & 2)) {
               const int y = b * p.M + mt * BM + q * 32;
@@ -350,36 +352,50 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         } else if (row_ok && col0 < p.N) {
+          // register-direct stores: every lane owns one output row and writes its 32 consecutive columns itself -- NO
+          // shared-memory traffic at all (the mainloop already runs at the smem bandwidth; a staged epilogue adds a write
+          // and a read of the whole tile to it).  256-bit stores = whole 32-byte sectors per lane.
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 32; j += 8) {
             const int col = col0 + j;
             if (col >= p.N) break;
-            float v[4];
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 8; ++e) {
               float x = __uint_as_float(r[j + e]) * p.alpha;
-              if (p.bias != nullptr) x += bias_s[c0 + j + e];
+              if (p.bias != nullptr) x += tc::ld_shared_f32(bias_u32 + 4 * (c0 + j + e));
               if (p.relu) x = fmaxf(x, 0.f);
               v[e] = x;
             }
             if (p.p_drop > 0.f) {
               // same element -> (counter, lane) mapping as relu_dropout_fwd_kernel: float4 index of [M,N]
-              uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col) >> 2), p.offset);
-              v[0] = rn.x >= thr ? v[0] * ks : 0.f; v[1] = rn.y >= thr ? v[1] * ks : 0.f;
-              v[2] = rn.z >= thr ? v[2] * ks : 0.f; v[3] = rn.w >= thr ? v[3] * ks : 0.f;
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4) {
+                uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col + 4 * h4) >> 2), p.offset);
+                v[4 * h4 + 0] = rn.x >= thr ? v[4 * h4 + 0] * ks : 0.f; v[4 * h4 + 1] = rn.y >= thr ? v[4 * h4 + 1] * ks : 0.f;
+                v[4 * h4 + 2] = rn.z >= thr ? v[4 * h4 + 2] * ks : 0.f; v[4 * h4 + 3] = rn.w >= thr ? v[4 * h4 + 3] * ks : 0.f;
+              }
             }
             if (p.round_out) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = tf32_rn(v[e]);
+              for (int e = 0; e < 8; ++e) v[e] = tf32_rn(v[e]);
             }
-            if (col + 3 < p.N && ((p.ldc & 3) == 0)) {
-              float4 o = make_float4(v[0], v[1], v[2], v[3]);
-              if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + col), o);
-              else *reinterpret_cast<float4*>(crow + col) = o;
+            if (p.wide8 && !p.accumulate && col + 7 < p.N) {
+              st_global_v8(crow + col, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
             } else {
-              for (int e = 0; e < 4 && col + e < p.N; ++e) {
-                if (p.accumulate) atomicAdd(crow + col + e, v[e]);
-                else crow[col + e] = v[e];
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4) {
+                const int c4 = col + 4 * h4;
+                if (c4 + 3 < p.N && ((p.ldc & 3) == 0)) {
+                  float4 o = make_float4(v[4 * h4], v[4 * h4 + 1], v[4 * h4 + 2], v[4 * h4 + 3]);
+                  if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + c4), o);
+                  else *reinterpret_cast<float4*>(crow + c4) = o;
+                } else {
+                  for (int e = 0; e < 4 && c4 + e < p.N; ++e) {
+                    if (p.accumulate) atomicAdd(crow + c4 + e, v[4 * h4 + e]);
+                    else crow[c4 + e] = v[4 * h4 + e];
+                  }
+                }
               }
             }
           }
@@ -442,8 +458,11 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
   p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
                 (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));
-  // measured (profiles/README.md, round 2): the direct form is SLOWER (QKV projection 120 vs 107 us), so TMA stores stay the default
-  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 0 : atoi(e); }
+  // PLANK_B200_GEMM_EPI: 0 = staged smem tile + TMA store, 1 = staged tile + coalesced st.global (measured slower than 0:
+  // 120 vs 107 us on the QKV projection), 2 = register-direct 256-bit stores, no smem traffic (split-K keeps TMA reduce-add)
+  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 2 : atoi(e); }
+  p.wide8 = (a.ldc % 8 == 0) && (((uintptr_t)a.c & 31) == 0) && (a.c_batch_stride % 8 == 0);
+  if (p.epi_direct == 2 && !p.accumulate) p.tma_store = 0;
   if (p.tma_store) {
     rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
     if (rc) return rc;

@@ -1,7 +1,7 @@
 """Event timeline of CTA 0 of the tensor-core GEMM (library built with PLANK_B200_NVCC_FLAGS=-DPA_GEMM_TRACE)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ['PLANK_B200_GEMM_DEBUG'] = '8'
+os.environ['PLANK_B200_GEMM_DEBUG'] = str(8 | int(os.environ.get('EXTRA_DEBUG', '0')))
 import torch
 from plankassembly_b200 import ops, _lib
 M, N, K = 32768, int(os.environ.get('GN', 1536)), int(os.environ.get('GK', 512))
