@@ -299,6 +299,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // additive key bias (0 / -inf: PAD keys and keys beyond Lk) of the WHOLE item, written once; the two tables
       // alternate between items, so one named barrier per item is all the elementwise warps need
       float* bias_it = bias_s + (ic & 1) * p.LkPad;
+      const uint32_t bias_u32 = tc::smem_u32(bias_it);
       uint32_t* flag_it = flags_s + (ic & 1) * 64;          // per 32-key group: 1 = every key valid (tiles of valid keys skip the bias)
 #pragma unroll
       for (int m = 0; m < KPT; ++m) {
@@ -350,7 +351,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               float mk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
-              const float4 b4 = *reinterpret_cast<const float4*>(bias_it + k0 + c0 + c);
+              const float4 b4 = tc::ld_shared_v4(bias_u32 + 4 * (k0 + c0 + c));      // explicit LDS (a generic LD.E costs ~17 more cycles)
               const float bz[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -673,6 +674,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         const bool diag = p.causal && (q0 < k0 + C::BKV - 1);
         const float* lse2 = stat_it + q0;
         const float* dl = stat_it + p.LqPad + q0;
+        const uint32_t lse2_u32 = tc::smem_u32(lse2), dl_u32 = tc::smem_u32(dl);
 #pragma unroll
         for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 32) {
           uint32_t rs[32], rd[32];
@@ -687,8 +689,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           } else if (!diag) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);     // per-query stats, 4 columns at a time
-              const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
+              const float4 l4 = tc::ld_shared_v4(lse2_u32 + 4 * (c0 + c));     // per-query stats, 4 columns at a time (explicit LDS)
+              const float4 d4 = tc::ld_shared_v4(dl_u32 + 4 * (c0 + c));
               const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -705,8 +707,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
               float mk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) mk[e] = ((mw >> (c + e)) & 1u) ? ks : 0.f;
-              const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + c);
-              const float4 d4 = *reinterpret_cast<const float4*>(dl + c0 + c);
+              const float4 l4 = tc::ld_shared_v4(lse2_u32 + 4 * (c0 + c));
+              const float4 d4 = tc::ld_shared_v4(dl_u32 + 4 * (c0 + c));
               const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {

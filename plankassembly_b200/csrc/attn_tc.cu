@@ -89,6 +89,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
   float* xch_s = reinterpret_cast<float*>(smem + C::kOffXch);
+  const uint32_t xch_u32 = tc::smem_u32(xch_s);
   int* flag_s = reinterpret_cast<int*>(smem + C::kOffFlag);      // [2 bufs][4 warps]: all 32 keys valid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars + 0;
@@ -288,6 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int qi = q0 + row;
       const int64_t row_global = ((int64_t)(b * p.H + h) * p.Lq + qi);
       const float* bias_it = bias_s + (itc & 1) * p.LkPad;
+      const uint32_t bias_u32 = tc::smem_u32(bias_it);
       const int* flag_it = flag_s + (itc & 1) * 64;
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
       float o_acc[32];
@@ -363,16 +365,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         } else {
 #pragma unroll
           for (int c = 0; c < HC; ++c) {
-            float v = s[c] + bias_it[k0 + half * HC + c];
+            float v = s[c] + tc::ld_shared_f32(bias_u32 + 4 * (k0 + half * HC + c));
             if (diag && k0 + half * HC + c > qi) v = -INFINITY;
             s[c] = v;
             mx = fmaxf(mx, v);
           }
         }
         if (!(p.debug & 8)) {
-          xch_s[(buf * 2 + half) * BQ + row] = mx;          // exchange the half-row maxima
+          tc::st_shared_f32(xch_u32 + 4 * ((buf * 2 + half) * BQ + row), mx);          // exchange the half-row maxima (explicit STS/LDS)
           TIMED_WAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));
-          mx = fmaxf(mx, xch_s[(buf * 2 + (half ^ 1)) * BQ + row]);
+          mx = fmaxf(mx, tc::ld_shared_f32(xch_u32 + 4 * ((buf * 2 + (half ^ 1)) * BQ + row)));
         }
         TRACE(trole, 4);
         const float m_new = fmaxf(m_run, mx);

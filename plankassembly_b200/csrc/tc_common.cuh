@@ -116,8 +116,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, fl
 }
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
