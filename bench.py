@@ -350,7 +350,8 @@ def run_decode(model, cfg, dev, world, rank, timed, args, workload):
     model.eval()
     from plankassembly_b200 import _lib
     with torch.no_grad():
-        out = model(resident[0])                       # warm-up: buffers, kernel attributes, CUDA-graph capture
+        for _ in range(2):                             # warm-up: buffers, kernel attributes, CUDA-graph capture, allocator pools
+            out = model(resident[0])
         n_tok = [0]
 
         def dec(i):

@@ -63,7 +63,7 @@ SIGNATURES = {
     'pa_embed_output_bwd': (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp]),
     'pa_add_ln_fwd': (i32, [vp, vp, vp, vp, vp, f32, f32, u64, u64, i64, i32, vp, vp, vp, vp, vp]),
     'pa_add_ln_bwd_workspace': (sz, [i64, i32]),
-    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'pa_add_ln_bwd': (i32, [vp, vp, vp, vp, vp, vp, f32, u64, u64, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
     'pa_relu_dropout_fwd': (i32, [vp, i64, f32, u64, u64, vp]),
     'pa_relu_dropout_bwd': (i32, [vp, vp, i64, f32, i32, vp]),
     'pa_relu_dropout_bwd_colsum': (i32, [vp, vp, i64, i32, f32, i32, vp, vp]),

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
 
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
-                                                                     const float2* __restrict__ stats, const float4* __restrict__ gamma,
+                                                                     const float2* __restrict__ stats, const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
                                                                      float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,7 +102,13 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
         float4 e = __ldg(dy2 + row * d4 + c);
         dyv.x += e.x; dyv.y += e.y; dyv.z += e.z; dyv.w += e.w;
       }
-      xh[i].x = (sv.x - st.x) * st.y; xh[i].y = (sv.y - st.x) * st.y; xh[i].z = (sv.z - st.x) * st.y; xh[i].w = (sv.w - st.x) * st.y;
+      if (beta != nullptr) {          // `s` holds the layer's OUTPUT y: x_hat = (y - beta) / gamma, no pre-norm tensor was saved
+        const float4 bt = __ldg(beta + c);
+        xh[i].x = gm.x != 0.f ? (sv.x - bt.x) / gm.x : 0.f; xh[i].y = gm.y != 0.f ? (sv.y - bt.y) / gm.y : 0.f;
+        xh[i].z = gm.z != 0.f ? (sv.z - bt.z) / gm.z : 0.f; xh[i].w = gm.w != 0.f ? (sv.w - bt.w) / gm.w : 0.f;
+      } else {
+        xh[i].x = (sv.x - st.x) * st.y; xh[i].y = (sv.y - st.x) * st.y; xh[i].z = (sv.z - st.x) * st.y; xh[i].w = (sv.w - st.x) * st.y;
+      }
       g[i].x = dyv.x * gm.x; g[i].y = dyv.y * gm.y; g[i].z = dyv.z * gm.z; g[i].w = dyv.w * gm.w;
       dg[i].x += dyv.x * xh[i].x; dg[i].y += dyv.y * xh[i].y; dg[i].z += dyv.z * xh[i].z; dg[i].w += dyv.w * xh[i].w;
       db[i].x += dyv.x; db[i].y += dyv.y; db[i].z += dyv.z; db[i].w += dyv.w;
@@ -201,7 +207,7 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias
   return PA_OK;
 }
 
-extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma, float p_drop,
+extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma, const float* beta, float p_drop,
                              uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, int round_da, float* dgamma,
                              float* dbeta, float* d_a_bias, void* partial, void* stream) {
   PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr && !(d_a_bias != nullptr && da == nullptr));
@@ -210,7 +216,7 @@ extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, 
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
   add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)dy2, (const float4*)s, (const float2*)stats,    \
-                                                         (const float4*)gamma, p_drop, seed, offset, rows, (float4*)dx, \
+                                                         (const float4*)gamma, (const float4*)beta, p_drop, seed, offset, rows, (float4*)dx, \
                                                          (float4*)da, round_da, d_a_bias != nullptr, (float*)partial)
   switch (d / 128) {
     case 1: LAUNCH(1); break;

@@ -153,7 +153,9 @@ class AddLayerNorm(Function):
     """y = LayerNorm_eps(x + dropout_p(a + a_bias)); a may be None (final norms); a_bias (may be None) is the
     bias of the linear that produced a, folded in here so that its gradient falls out of the backward kernel.
     want_r: also return the TF32-rounded copy of y that feeds the next tensor-core GEMM;
-    round_da: the gradient wrt a feeds tensor-core GEMMs only, so it is written rounded."""
+    round_da: the gradient wrt a feeds tensor-core GEMMs only, so it is written rounded.
+    Nothing but the OUTPUT is saved for the backward (the TF32 copy where there is one -- the next GEMM keeps it alive
+    anyway): x_hat = (y - beta) / gamma, so the forward writes no pre-norm tensor."""
 
     @staticmethod
     def forward(ctx, x, a, a_bias, gamma, beta, eps, p_drop, want_r=False, round_da=False):
@@ -165,12 +167,11 @@ class AddLayerNorm(Function):
         y = torch.empty_like(x)
         y_r = torch.empty_like(x) if want_r else None
         need_grad = any(ctx.needs_input_grad)
-        s = torch.empty_like(x) if (need_grad and a is not None) else None
         stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
         seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
         call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), _ptr(a_bias), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
-             seed, off, rows, d, y.data_ptr(), _ptr(y_r), _ptr(s), _ptr(stats), _stream())
-        ctx.save_for_backward(s if s is not None else x, stats, gamma)
+             seed, off, rows, d, y.data_ptr(), _ptr(y_r), None, _ptr(stats), _stream())
+        ctx.save_for_backward(y_r if y_r is not None else y, stats, gamma, beta)
         ctx.has_a, ctx.p, ctx.seed, ctx.off = a is not None, (p_drop if a is not None else 0.0), seed, off
         ctx.round_da, ctx.has_bias = round_da, a_bias is not None
         return (y, y_r) if want_r else y
@@ -178,19 +179,19 @@ class AddLayerNorm(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy, dy_r=None):
-        s, stats, gamma = ctx.saved_tensors
+        yo, stats, gamma, beta = ctx.saved_tensors
         dy = dy.contiguous()
         dy_r = dy_r.contiguous() if dy_r is not None else None
-        d = s.shape[-1]
-        rows = s.numel() // d
-        dx = torch.empty_like(s)
-        da = torch.empty_like(s) if (ctx.has_a and (ctx.p > 0 or ctx.round_da or ctx.has_bias)) else None
+        d = yo.shape[-1]
+        rows = yo.numel() // d
+        dx = torch.empty_like(yo)
+        da = torch.empty_like(yo) if (ctx.has_a and (ctx.p > 0 or ctx.round_da or ctx.has_bias)) else None
         dgamma = _zeros(gamma.shape, gamma.device)
         dbeta = _zeros(gamma.shape, gamma.device)
         dabias = _zeros(gamma.shape, gamma.device) if ctx.has_bias else None
-        ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=s.device, dtype=torch.uint8)
-        call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), s.data_ptr(), stats.data_ptr(), gamma.data_ptr(), ctx.p, ctx.seed,
-             ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
+        ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=yo.device, dtype=torch.uint8)
+        call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), yo.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ctx.p,
+             ctx.seed, ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
              ws.data_ptr(), _stream(), launches=2)
         if ctx.has_a and da is None:
             da = dx                      # no dropout, no rounding: same gradient flows to both summands
