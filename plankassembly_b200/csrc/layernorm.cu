@@ -104,8 +104,9 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
       }
       if (beta != nullptr) {          // `s` holds the layer's OUTPUT y: x_hat = (y - beta) / gamma, no pre-norm tensor was saved
         const float4 bt = __ldg(beta + c);
-        xh[i].x = gm.x != 0.f ? (sv.x - bt.x) / gm.x : 0.f; xh[i].y = gm.y != 0.f ? (sv.y - bt.y) / gm.y : 0.f;
-        xh[i].z = gm.z != 0.f ? (sv.z - bt.z) / gm.z : 0.f; xh[i].w = gm.w != 0.f ? (sv.w - bt.w) / gm.w : 0.f;
+        // fast division (MUFU.RCP + FMUL): the kernel must stay HBM-bound; a gamma of exactly 0 gives x_hat = 0
+        xh[i].x = gm.x != 0.f ? __fdividef(sv.x - bt.x, gm.x) : 0.f; xh[i].y = gm.y != 0.f ? __fdividef(sv.y - bt.y, gm.y) : 0.f;
+        xh[i].z = gm.z != 0.f ? __fdividef(sv.z - bt.z, gm.z) : 0.f; xh[i].w = gm.w != 0.f ? __fdividef(sv.w - bt.w, gm.w) : 0.f;
       } else {
         xh[i].x = (sv.x - st.x) * st.y; xh[i].y = (sv.y - st.x) * st.y; xh[i].z = (sv.z - st.x) * st.y; xh[i].w = (sv.w - st.x) * st.y;
       }

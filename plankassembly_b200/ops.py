@@ -149,6 +149,9 @@ class EmbedOutput(Function):
         return None, None, None, None, gv, gc, gp
 
 
+LN_SAVE_PRENORM = os.environ.get('PLANK_B200_LN_SAVE', 'y') == 's'
+
+
 class AddLayerNorm(Function):
     """y = LayerNorm_eps(x + dropout_p(a + a_bias)); a may be None (final norms); a_bias (may be None) is the
     bias of the linear that produced a, folded in here so that its gradient falls out of the backward kernel.
@@ -168,10 +171,12 @@ class AddLayerNorm(Function):
         y_r = torch.empty_like(x) if want_r else None
         need_grad = any(ctx.needs_input_grad)
         stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32) if need_grad else None
+        s = torch.empty_like(x) if (need_grad and LN_SAVE_PRENORM) else None        # A/B switch: round 1 saved the pre-norm sum
         seed, off = RNG.next() if (p_drop > 0 and a is not None) else (0, 0)
         call('pa_add_ln_fwd', x.data_ptr(), _ptr(a), _ptr(a_bias), gamma.data_ptr(), beta.data_ptr(), eps, p_drop if a is not None else 0.0,
-             seed, off, rows, d, y.data_ptr(), _ptr(y_r), None, _ptr(stats), _stream())
-        ctx.save_for_backward(y_r if y_r is not None else y, stats, gamma, beta)
+             seed, off, rows, d, y.data_ptr(), _ptr(y_r), _ptr(s), _ptr(stats), _stream())
+        ctx.from_y = s is None
+        ctx.save_for_backward(s if s is not None else (y_r if y_r is not None else y), stats, gamma, beta)
         ctx.has_a, ctx.p, ctx.seed, ctx.off = a is not None, (p_drop if a is not None else 0.0), seed, off
         ctx.round_da, ctx.has_bias = round_da, a_bias is not None
         return (y, y_r) if want_r else y
@@ -190,7 +195,7 @@ class AddLayerNorm(Function):
         dbeta = _zeros(gamma.shape, gamma.device)
         dabias = _zeros(gamma.shape, gamma.device) if ctx.has_bias else None
         ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=yo.device, dtype=torch.uint8)
-        call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), yo.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ctx.p,
+        call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), yo.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr() if ctx.from_y else None, ctx.p,
              ctx.seed, ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
              ws.data_ptr(), _stream(), launches=2)
         if ctx.has_a and da is None:
