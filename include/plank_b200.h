@@ -115,7 +115,7 @@ typedef struct {
   int round_out;               /* write O rounded to TF32 (it feeds a tensor-core GEMM) */
   const uint32_t* drop_rows;   /* keep-bit masks from pa_dropout_mask (required by impl 1 when p_drop > 0) */
   const uint32_t* drop_cols;
-  const int32_t* kv_len;       /* optional [B] (impl 1): every key j >= kv_len[b] is PAD in kpm -> whole key tiles beyond it are
+  const int32_t* kv_len;       /* optional [B] (both impls, forward): every key j >= kv_len[b] is PAD in kpm -> whole key tiles beyond it are
                                   skipped (ragged batches padded to a fixed length, LineDataset layout); NULL = Lk */
 } pa_attn_fwd_args;
 int pa_attn_fwd(const pa_attn_fwd_args* args, void* stream);

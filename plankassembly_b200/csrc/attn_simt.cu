@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_simt_kernel(pa_attn_fwd_args A) {
 #pragma unroll
     for (int w = 0; w < W; ++w) o[r][w] = 0.f;
   }
-  const int kv_end = A.causal ? min(A.Lk, q0 + BM) : A.Lk;
+  int kv_end = A.causal ? min(A.Lk, q0 + BM) : A.Lk;
+  // keys beyond kv_len[b] (1 + last non-PAD key) carry -inf: whole key tiles of padding are skipped (exact)
+  if (A.kv_len != nullptr && A.kpm != nullptr) kv_end = min(kv_end, max(A.kv_len[b], 1));
   for (int k0 = 0; k0 < kv_end; k0 += BN) {
     __syncthreads();
     load_tile<DH, true>(Ks, kp, A.ldk, k0, A.Lk);

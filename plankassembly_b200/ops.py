@@ -310,7 +310,7 @@ def _attn_fwd(q, k, v, ldq, ldk, ldv, B, H, Lq, Lk, dh, kpm, causal, p_drop, see
         masks = _drop_masks(B, H, Lq, Lk, p_drop, seed, off, device) if (impl == 1 and p_drop > 0) else (None, None)
     a = AttnFwdArgs(q, k, v, ldq, ldk, ldv, o.data_ptr(), H * dh, _ptr(lse), _ptr(kpm), B, H, Lq, Lk, dh, int(causal),
                     dh ** -0.5, p_drop, seed, off, impl, int(rnd), _ptr(masks[0]), _ptr(masks[1]),
-                    _ptr(_kv_len(kpm)) if impl == 1 else None)
+                    _ptr(_kv_len(kpm)))
     call('pa_attn_fwd', C.byref(a), _stream())
     return o, lse, masks
 
@@ -327,6 +327,16 @@ def _attn_bwd(q, k, v, ldq, ldk, ldv, o, do, lse, dq, dk, dv, lddq, lddk, lddv, 
     call('pa_attn_bwd', C.byref(a), _stream(), launches=3)
 
 
+TC_MAX_LQ, TC_MAX_LK = 1280, 2048      # shared-memory tables of the tensor-core attention kernels (include/plank_b200.h)
+
+
+def _fit_impl(impl, Lq, Lk):
+    """The tensor-core attention kernels keep per-item tables in shared memory (key bias: Lk <= 2048; query statistics of the
+    dK/dV kernel: Lq <= 1280).  Longer sequences than any reference config has (MAX_INPUT_LENGTH 1200) are served by the
+    fp32 CUDA-core kernels instead of failing."""
+    return 0 if (impl == 1 and (Lq > TC_MAX_LQ or Lk > TC_MAX_LK)) else impl
+
+
 class SelfAttention(Function):
     """K3/K4: attention core over the packed in-projection output qkv [B,L,3d].
     `bias` (may be None) is the in-projection bias PARAMETER: it is not used in the forward (the GEMM epilogue
@@ -339,6 +349,7 @@ class SelfAttention(Function):
         qkv = qkv.contiguous()
         B, L, d3 = qkv.shape
         d = d3 // 3
+        impl = _fit_impl(impl, L, L)
         pre = MASKS.take(B, H, L, L, p_drop) if (impl == 1 and p_drop > 0) else None
         seed, off, pm = pre if pre is not None else ((*RNG.next(), None) if p_drop > 0 else (0, 0, None))
         base = qkv.data_ptr()
@@ -375,6 +386,7 @@ class CrossAttention(Function):
         q, kv = q.contiguous(), kv.contiguous()
         B, Lq, d = q.shape
         Lk = kv.shape[1]
+        impl = _fit_impl(impl, Lq, Lk)
         pre = MASKS.take(B, H, Lq, Lk, p_drop) if (impl == 1 and p_drop > 0) else None
         seed, off, pm = pre if pre is not None else ((*RNG.next(), None) if p_drop > 0 else (0, 0, None))
         kb = kv.data_ptr()

@@ -214,3 +214,22 @@ def test_kv_len_skips_padding_tiles(H, dh, L, causal, valid):
     # gradients of PAD keys are exactly zero (their dK/dV items are skipped, not computed)
     for b, n in enumerate(valid):
         assert gk[b, n:].abs().max().item() == 0.0 if n < L else True
+
+
+def test_sequences_beyond_the_tensor_core_tables_fall_back():
+    """Lq > 1280 / Lk > 2048 exceed the shared-memory tables of the tensor-core kernels: ops route such calls to the fp32
+    CUDA-core kernels (forward and backward) instead of raising."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, H, dh, L = 1, 2, 64, 2304
+    d = H * dh
+    qkv = torch.randn(B, L, 3 * d, generator=g).cuda().requires_grad_(True)
+    kpm = torch.zeros(B, L, dtype=torch.uint8).cuda()
+    kpm[:, 2100:] = 1
+    o = ops.SelfAttention.apply(qkv, None, kpm, H, False, 0.0, 1, True)
+    o.square().sum().backward()
+    q, k, v = [t.view(B, L, H, dh).transpose(1, 2).double() for t in qkv.detach().cpu().split(d, dim=-1)]
+    sc = q @ k.transpose(-1, -2) / dh ** 0.5
+    sc[..., 2100:] = float('-inf')
+    ref = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B, L, d)
+    assert rel_err(o.detach().cpu(), ref) < 1e-3 and torch.isfinite(qkv.grad).all()
