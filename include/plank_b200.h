@@ -61,8 +61,8 @@ int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias, const flo
                   float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
                   float* stats, void* stream);
 /* dx = grad wrt x (and wrt s); da = dropout-masked copy (may be NULL); dgamma/dbeta are
- * accumulated (+=).  dy2 (may be NULL) is a second incoming gradient added to dy (the TF32 copy's).  partial = workspace of
- * pa_add_ln_bwd_workspace(rows,d) bytes.  beta == NULL: `s` is the pre-norm sum the forward saved; beta != NULL: `s` is the
+ * accumulated (+=, vector RED per block: 16-byte aligned).  dy2 (may be NULL) is a second incoming gradient added to dy (the
+ * TF32 copy's).  partial: unused since ABI 3 (pass NULL; pa_add_ln_bwd_workspace returns 0).  beta == NULL: `s` is the pre-norm sum the forward saved; beta != NULL: `s` is the
  * layer's OUTPUT y (or its TF32 copy, which the next GEMM keeps alive anyway) and x_hat is recovered as (y - beta) / gamma,
  * so the forward need not write a pre-norm tensor at all (20 % less LayerNorm traffic, one [rows,d] tensor less per layer). */
 size_t pa_add_ln_bwd_workspace(int64_t rows, int d);

@@ -8,7 +8,14 @@
 #include "common.cuh"
 
 constexpr int kLnWarps = 4;
-static inline int ln_max_blocks() { return pa_num_sms() * 4; }
+// Blocks of 4 warps per SM for the row-per-warp LayerNorm kernels.  The ncu capture of round 2 showed add_ln_fwd at 3.4 TB/s
+// with 24 % of the warp slots occupied (4 blocks per SM: too few rows in flight to cover the HBM latency, the loads of a
+// warp's next row are only issued after its current row is stored), hence 16; PLANK_B200_LN_BLOCKS_PER_SM overrides.
+#include <stdlib.h>
+static inline int ln_max_blocks() {
+  static const int per_sm = [] { const char* e = getenv("PLANK_B200_LN_BLOCKS_PER_SM"); int v = e ? atoi(e) : 16; return v > 0 ? v : 16; }();
+  return pa_num_sms() * per_sm;
+}
 
 // Sub-block output dropout of the residual rows: 16 random bits per element, one Philox4x32-10 call per PAIR of float4
 // chunks of a lane (chunk i uses the low halves of the four words when i is even, the high halves when it is odd).
@@ -81,7 +88,8 @@ template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
                                                                      const float2* __restrict__ stats, const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
-                                                                     float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial) {
+                                                                     float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial,
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dabias) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32, d = NV * 128;
   const float inv_d = 1.f / (float)d;
@@ -146,8 +154,10 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
 #pragma unroll
   for (int i = 0; i < NV; ++i) { sm[warp][0][lane + i * 32] = dg[i]; sm[warp][1][lane + i * 32] = db[i]; sm[warp][2][lane + i * 32] = dab[i]; }
   __syncthreads();
-  float4* out = reinterpret_cast<float4*>(partial) + (int64_t)blockIdx.x * 3 * d4;
-  for (int i = threadIdx.x; i < 3 * d4; i += blockDim.x) {
+  // one vector RED per block and column group straight into dgamma / dbeta / (linear bias) -- replaces the per-block
+  // partial rows + a second reduction kernel (32 extra launches and 0.38 ms per step); `partial` is unused now
+  (void)partial;
+  for (int i = threadIdx.x; i < (want_dabias ? 3 : 2) * d4; i += blockDim.x) {
     int which = i / d4, c = i % d4;
     float4 acc = sm[0][which][c];
 #pragma unroll
@@ -155,26 +165,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
       float4 t = sm[w][which][c];
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    out[i] = acc;
-  }
-}
-
-// dgamma/dbeta += sum over blocks of partial
-__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblocks, int d, float* dgamma, float* dbeta, float* dabias) {
-  __shared__ float sm[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + cx;                 // column of the [3d] (gamma | beta | linear bias) vector
-  const int ncol = dabias != nullptr ? 3 * d : 2 * d;
-  float acc = 0.f;
-  if (i < ncol)
-    for (int b = ry; b < nblocks; b += 8) acc += partial[(int64_t)b * 3 * d + i];
-  sm[ry][cx] = acc;
-  __syncthreads();
-  if (ry == 0 && i < ncol) {
-    float t = 0.f;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) t += sm[r][cx];
-    if (i < d) dgamma[i] += t; else if (i < 2 * d) dbeta[i - d] += t; else dabias[i - 2 * d] += t;
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dabias);
+    atomicAdd(reinterpret_cast<float4*>(dst) + c, acc);
   }
 }
 
@@ -183,7 +175,7 @@ static int ln_grid(int64_t rows) {
   return (int)(nb < ln_max_blocks() ? nb : ln_max_blocks());
 }
 
-extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { return (size_t)ln_grid(rows) * 3 * d * sizeof(float); }
+extern "C" size_t pa_add_ln_bwd_workspace(int64_t rows, int d) { (void)rows; (void)d; return 0; }   // kept for ABI stability: no workspace needed any more
 
 extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias, const float* gamma, const float* beta, float eps,
                              float p_drop, uint64_t seed, uint64_t offset, int64_t rows, int d, float* y, float* y_tf32, float* s,
@@ -211,14 +203,15 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias
 extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, const float* stats, const float* gamma, const float* beta, float p_drop,
                              uint64_t seed, uint64_t offset, int64_t rows, int d, float* dx, float* da, int round_da, float* dgamma,
                              float* dbeta, float* d_a_bias, void* partial, void* stream) {
-  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && partial != nullptr && !(d_a_bias != nullptr && da == nullptr));
+  PA_CHECK_ARG(rows >= 0 && d % 128 == 0 && d <= 1024 && dgamma != nullptr && dbeta != nullptr && !(d_a_bias != nullptr && da == nullptr));
+  PA_CHECK_ARG((((uintptr_t)dgamma | (uintptr_t)dbeta | (uintptr_t)d_a_bias) & 15) == 0);
   if (rows == 0) return PA_OK;
   int grid = ln_grid(rows);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(NV)                                                                                                   \
   add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)dy2, (const float4*)s, (const float2*)stats,    \
                                                          (const float4*)gamma, (const float4*)beta, p_drop, seed, offset, rows, (float4*)dx, \
-                                                         (float4*)da, round_da, d_a_bias != nullptr, (float*)partial)
+                                                         (float4*)da, round_da, d_a_bias != nullptr, (float*)partial, dgamma, dbeta, d_a_bias)
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -227,8 +220,6 @@ extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, 
     default: pa_set_error("pa_add_ln_bwd: d=%d unsupported", d); return PA_ERR_UNSUPPORTED;
   }
 #undef LAUNCH
-  PA_CHECK_LAUNCH();
-  ln_param_reduce_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>((const float*)partial, grid, d, dgamma, dbeta, d_a_bias);
   PA_CHECK_LAUNCH();
   return PA_OK;
 }

@@ -194,10 +194,9 @@ class AddLayerNorm(Function):
         dgamma = _zeros(gamma.shape, gamma.device)
         dbeta = _zeros(gamma.shape, gamma.device)
         dabias = _zeros(gamma.shape, gamma.device) if ctx.has_bias else None
-        ws = torch.empty(_lib.load().pa_add_ln_bwd_workspace(rows, d), device=yo.device, dtype=torch.uint8)
         call('pa_add_ln_bwd', dy.data_ptr(), _ptr(dy_r), yo.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr() if ctx.from_y else None, ctx.p,
              ctx.seed, ctx.off, rows, d, dx.data_ptr(), _ptr(da), int(ctx.round_da), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dabias),
-             ws.data_ptr(), _stream(), launches=2)
+             None, _stream())
         if ctx.has_a and da is None:
             da = dx                      # no dropout, no rounding: same gradient flows to both summands
         return dx, (da if ctx.has_a else None), dabias, dgamma, dbeta, None, None, None, None
