@@ -10,10 +10,10 @@
 constexpr int kLnWarps = 4;
 // Blocks of 4 warps per SM for the row-per-warp LayerNorm kernels.  The ncu capture of round 2 showed add_ln_fwd at 3.4 TB/s
 // with 24 % of the warp slots occupied (4 blocks per SM: too few rows in flight to cover the HBM latency, the loads of a
-// warp's next row are only issued after its current row is stored), hence 16; PLANK_B200_LN_BLOCKS_PER_SM overrides.
+// warp's next row are only issued after its current row is stored), hence 8 (measured per step: 4 -> 22.71 ms, 8 -> 21.90, 16 -> 21.95, 32 -> 22.06); PLANK_B200_LN_BLOCKS_PER_SM overrides.
 #include <stdlib.h>
 static inline int ln_max_blocks() {
-  static const int per_sm = [] { const char* e = getenv("PLANK_B200_LN_BLOCKS_PER_SM"); int v = e ? atoi(e) : 16; return v > 0 ? v : 16; }();
+  static const int per_sm = [] { const char* e = getenv("PLANK_B200_LN_BLOCKS_PER_SM"); int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
   return pa_num_sms() * per_sm;
 }
 
