@@ -52,7 +52,10 @@ class GreedyDecoder:
         # large batches are decoded as independent CHAINS of this many sequences, one CUDA stream (= one parallel branch of
         # the captured graph) each: a chain's small-M GEMMs occupy 6-24 SMs, so several chains together fill the machine
         # and one chain's K/V streaming (HBM) overlaps another chain's projections (tensor cores)
-        self.chain_rows = int(os.environ.get('PLANK_B200_DECODE_CHAIN_ROWS', '128'))
+        # Measured (profiles/README.md): B=256 -> 8 chains of 32 with the fp32 FMA projections 207 k tok/s (2 chains of 128
+        # with 3xTF32: 112 k); B=1024 -> 8 chains of 128 with 3xTF32 251 k (16 chains of 64 with fp32 FMA: 217 k).
+        # Default: chains of 128 from batch 1024 on, chains of 32 below; PLANK_B200_DECODE_CHAIN_ROWS overrides.
+        self.chain_rows = int(os.environ.get('PLANK_B200_DECODE_CHAIN_ROWS', '0'))
         self._key = None
         self.graph = None
         self._lin_out = {}
@@ -88,7 +91,8 @@ class GreedyDecoder:
             self.part = torch.empty(ws // 4, device=device, dtype=torch.float32)
         self._key, self.graph = key, None
         self._lin_out, self._x3 = {}, {}
-        n_chains = max(1, min(16, B // max(1, self.chain_rows)))
+        rows = self.chain_rows if self.chain_rows > 0 else (128 if B >= 1024 else 32)
+        n_chains = max(1, min(16, B // rows))
         per = -(-B // n_chains)
         self.chains = [(c0, min(B, c0 + per)) for c0 in range(0, B, per)]
         self.streams = [torch.cuda.Stream(device=device) for _ in self.chains] if len(self.chains) > 1 else []
