@@ -71,18 +71,21 @@ def _require_cuda(*ts):
 
 
 class DropoutState:
-    """Seed + per-site Philox offsets.  Every dropout site of every forward draws a fresh offset;
-    backward kernels regenerate the masks from (seed, offset)."""
+    """(seed, offset) for every dropout site, drawn from torch's own CUDA generator state.
 
-    def __init__(self):
-        self.seed = None
-        self.counter = 0
+    Every site of every forward takes the generator's current Philox offset as its stream id and advances the generator, as
+    a torch dropout kernel would; backward kernels regenerate the masks from the (seed, offset) they saved.  The masks are
+    therefore a function of torch's RNG state: `torch.manual_seed` / `seed_everything` reseed them, and
+    `torch.cuda.get_rng_state` / `set_rng_state` (checkpoint resume) reproduce them -- round 1 kept a private counter seeded
+    once from `torch.initial_seed()`, which a later `manual_seed` or a resume could not reach."""
+
+    STEP = 4          # torch keeps Philox offsets at multiples of 4
 
     def next(self):
-        if self.seed is None:
-            self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        self.counter += 1
-        return self.seed, self.counter
+        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        off = gen.get_offset()
+        gen.set_offset(off + self.STEP)
+        return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, off // self.STEP + 1
 
 
 RNG = DropoutState()

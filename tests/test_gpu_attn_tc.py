@@ -98,9 +98,9 @@ def test_tc_dropout_matches_simt_mask():
     q, k = torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)
     v = torch.eye(L)[None, :, None, :].expand(B, L, H, dh).reshape(B, L, d)
     qkv = tf32_round(torch.cat([q, k, v], -1))
-    ops.RNG.seed, ops.RNG.counter = 1234, 100
+    torch.manual_seed(1234)            # same torch RNG state => same (seed, offset) => same mask in both kernels
     o_tc = ops.SelfAttention.apply(qkv, None, None, H, False, p, 1)
-    ops.RNG.seed, ops.RNG.counter = 1234, 100
+    torch.manual_seed(1234)            # same torch RNG state => same (seed, offset) => same mask in both kernels
     o_simt = ops.SelfAttention.apply(qkv, None, None, H, False, p, 0)
     assert torch.equal(o_tc > 0, o_simt > 0)
     assert abs((o_tc > 0).float().mean().item() - (1 - p)) < 2e-2
@@ -174,7 +174,7 @@ def test_tc_bwd_dropout_matches_fp32_kernels():
     grads = []
     for impl in (1, 0):
         qkv = base.clone().requires_grad_(True)
-        ops.RNG.seed, ops.RNG.counter = 99, 7
+        torch.manual_seed(99)
         out = ops.SelfAttention.apply(qkv, None, None, H, True, p, impl)
         (out * w).sum().backward()
         grads.append(qkv.grad.clone())

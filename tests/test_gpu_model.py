@@ -237,6 +237,33 @@ def test_dropout_training_statistics():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
 
 
+def test_dropout_follows_torch_rng_state():
+    """Dropout masks are a function of torch's CUDA generator state: reseeding or restoring the state reproduces the step
+    (what `seed_everything` and a checkpoint resume rely on), a different seed changes it."""
+    cfg = syn.tiny_cfg(dropout=0.2)
+    batch = to_dev(syn.batch_for(cfg, range(4)))
+    m = build(cfg, syn.init_state_dict(cfg)).train()
+
+    def step_loss():
+        m.zero_grad(set_to_none=True)
+        out = m(batch)
+        out['loss'].backward()
+        return out['loss'].item(), m.vocab_head.weight.grad.clone()
+
+    torch.manual_seed(5)
+    l1, g1 = step_loss()
+    state = torch.cuda.get_rng_state()
+    l2, g2 = step_loss()
+    torch.manual_seed(5)
+    l1b, g1b = step_loss()
+    assert l1 == l1b and torch.equal(g1, g1b) and l1 != l2
+    torch.cuda.set_rng_state(state)
+    l2b, g2b = step_loss()
+    assert l2 == l2b and torch.equal(g2, g2b)
+    torch.manual_seed(6)
+    assert step_loss()[0] != l1
+
+
 def test_cpu_tensors_fail_loudly():
     from plankassembly_b200._lib import PlankB200Error
     from plankassembly_b200.models import build_model
