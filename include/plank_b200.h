@@ -160,6 +160,11 @@ typedef struct {
   int batch; int64_t a_batch_rows, b_batch_rows, c_batch_stride;
   int split_k; int accumulate;
   int round_out;               /* write C rounded to TF32 (when C only feeds tensor-core operands) */
+  /* Fused FFN activation backward (replaces a separate relu/dropout-backward pass over the [tokens, ff] gradient; batch = 1,
+   * N % 32 == 0, no split-K).  Forward GEMM (relu [+ dropout] epilogue): mask_out [M, N/32] receives one bit per output,
+   * set where C > 0.  Backward dX GEMM: mask_in = that plane, C <- mask ? C * mask_scale : 0 (mask_scale = 1/(1-p)), and
+   * colsum [N] (may be NULL) accumulates the column sums of the masked C -- the bias gradient of the forward linear. */
+  uint32_t* mask_out; const uint32_t* mask_in; float* colsum; float mask_scale;
 } pa_gemm_args;
 int pa_gemm_tf32(const pa_gemm_args* args, void* stream);
 

@@ -32,7 +32,8 @@ class GemmArgs(C.Structure):
     _fields_ = [('a', vp), ('lda', i64), ('a_mn', i32), ('b', vp), ('ldb', i64), ('b_mn', i32),
                 ('c', vp), ('ldc', i64), ('bias', vp), ('relu', i32), ('p_drop', f32), ('seed', u64), ('offset', u64),
                 ('alpha', f32), ('M', i32), ('N', i32), ('K', i32), ('batch', i32),
-                ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32), ('round_out', i32)]
+                ('a_batch_rows', i64), ('b_batch_rows', i64), ('c_batch_stride', i64), ('split_k', i32), ('accumulate', i32), ('round_out', i32),
+                ('mask_out', vp), ('mask_in', vp), ('colsum', vp), ('mask_scale', f32)]
 
 
 fp = C.c_void_p

@@ -58,6 +58,7 @@ struct GemmParams {
   int tma_store;          // epilogue stores through smem + TMA (needs a 16-byte row pitch)
   int epi_direct;         // 1: through the same swizzled smem tile and coalesced st.global.v4 (measured slower); 2: register-direct
   int wide8;              // C rows are 32-byte aligned: the register-direct epilogue may use 256-bit stores
+  uint32_t* mask_out; const uint32_t* mask_in; float* colsum; float mask_scale;   // fused FFN activation backward (see the header)
   int m_tiles, n_tiles;
 };
 
@@ -351,20 +352,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               tc::tma_store_commit();
             }
           }
-        } else if (row_ok && col0 < p.N) {
+        } else if (col0 < p.N && (row_ok || p.colsum != nullptr)) {
           // register-direct stores: every lane owns one output row and writes its 32 consecutive columns itself -- NO
           // shared-memory traffic at all (the mainloop already runs at the smem bandwidth; a staged epilogue adds a write
           // and a read of the whole tile to it).  256-bit stores = whole 32-byte sectors per lane.
+          // Fused FFN activation backward: a lane's 32 columns are exactly one word of the relu/dropout bit plane.
+          const int mask_ld = p.N >> 5;
+          const uint32_t min_w = (p.mask_in != nullptr && row_ok) ? __ldg(p.mask_in + (int64_t)row * mask_ld + (col0 >> 5)) : 0u;
+          uint32_t mout_w = 0u;
+          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             const int col = col0 + j;
-            if (col >= p.N) break;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float x = __uint_as_float(r[j + e]) * p.alpha;
               if (p.bias != nullptr) x += tc::ld_shared_f32(bias_u32 + 4 * (c0 + j + e));
               if (p.relu) x = fmaxf(x, 0.f);
+              if (p.mask_in != nullptr) x = ((min_w >> (j + e)) & 1u) ? x * p.mask_scale : 0.f;
               v[e] = x;
             }
             if (p.p_drop > 0.f) {
@@ -380,6 +386,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = tf32_rn(v[e]);
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[j + e] = (row_ok && col + e < p.N) ? v[e] : 0.f;
+              mout_w |= (uint32_t)(v[e] > 0.f) << (j + e);
+            }
+            if (!row_ok || col >= p.N) continue;
             if (p.wide8 && !p.accumulate && col + 7 < p.N) {
               st_global_v8(crow + col, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
             } else {
@@ -398,6 +410,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
               }
             }
+          }
+          if (p.mask_out != nullptr && row_ok) p.mask_out[(int64_t)row * mask_ld + (col0 >> 5)] = mout_w;
+          if (p.colsum != nullptr) {          // warp-uniform: all 32 lanes are here; column sums over the warp's 32 rows
+            const float cs = warp_colsum32(f, lane);
+            if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
           }
         }
       }
@@ -463,6 +480,8 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 2 : atoi(e); }
   p.wide8 = (a.ldc % 8 == 0) && (((uintptr_t)a.c & 31) == 0) && (a.c_batch_stride % 8 == 0);
   if (p.epi_direct == 2 && !p.accumulate) p.tma_store = 0;
+  p.mask_out = a.mask_out; p.mask_in = a.mask_in; p.colsum = a.colsum; p.mask_scale = a.mask_scale;
+  if (p.mask_out != nullptr || p.mask_in != nullptr || p.colsum != nullptr) p.tma_store = 0;      // lives in the register-direct epilogue
   if (p.tma_store) {
     rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
     if (rc) return rc;
@@ -537,6 +556,8 @@ extern "C" int pa_gemm_tf32(const pa_gemm_args* a, void* stream) {
   PA_CHECK_ARG(!(a->batch > 1 && (a->a_mn || a->b_mn) && a->K % 32 != 0));
   PA_CHECK_ARG(!(a->split_k > 1 && !a->accumulate));
   PA_CHECK_ARG(!(a->accumulate && (a->bias != nullptr || a->relu || a->p_drop > 0.f)));
+  if (a->mask_out != nullptr || a->mask_in != nullptr || a->colsum != nullptr)
+    PA_CHECK_ARG(a->batch <= 1 && a->N % 32 == 0 && !a->accumulate && a->split_k <= 1);
   cudaStream_t st = (cudaStream_t)stream;
   const bool wide = a->N > 128 && (a->N % 256 == 0 || a->N > 1024);
   if (!a->a_mn && !a->b_mn) return wide ? launch<256, false, false>(*a, st) : launch<128, false, false>(*a, st);

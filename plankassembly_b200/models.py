@@ -158,6 +158,11 @@ class PlankModel(nn.Module):
         return y, y
 
     def _ffn(self, layer, x_r, tf):
+        ff, d = layer.linear1.weight.shape
+        if tf and ops.FFN_FUSED and ff % 32 == 0:
+            # both projections and the activation as one autograd node (fused activation backward, ops.FFN)
+            return ops.FFN.apply(x_r, layer.linear1.weight, layer.linear1.bias, ops.tf32_weight(layer.linear1.weight),
+                                 layer.linear2.weight, ops.tf32_weight(layer.linear2.weight), self._p())
         h = ops.linear(x_r, layer.linear1.weight, layer.linear1.bias, relu=True, p_drop=self._p(), tf32=tf, round_out=True)
         # TF32 path: linear2 runs bias-free, its bias is folded into the following residual+LayerNorm kernel
         return ops.linear(h, layer.linear2.weight, None if tf else layer.linear2.bias, tf32=tf, round_dx=True)

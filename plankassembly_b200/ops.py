@@ -418,11 +418,13 @@ class CrossAttention(Function):
 
 
 def gemm_tf32(a, b, c, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, bias=None, relu=False, p_drop=0.0, seed=0, off=0,
-              alpha=1.0, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, split_k=1, accumulate=False, round_out=False):
-    """C = alpha * op(A) op(B)^T (+bias)(relu)(dropout) on the tcgen05 tensor cores (TF32 in, FP32 acc)."""
+              alpha=1.0, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, split_k=1, accumulate=False, round_out=False,
+              mask_out=None, mask_in=None, colsum=None, mask_scale=0.0):
+    """C = alpha * op(A) op(B)^T (+bias)(relu)(dropout) on the tcgen05 tensor cores (TF32 in, FP32 acc).
+    mask_out / mask_in / colsum / mask_scale: the fused FFN activation backward (include/plank_b200.h, pa_gemm_args)."""
     g = GemmArgs(a.data_ptr(), lda, int(a_mn), b.data_ptr(), ldb, int(b_mn), c.data_ptr(), ldc, _ptr(bias), int(relu), p_drop,
                  seed, off, alpha, M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, split_k, int(accumulate),
-                 int(round_out))
+                 int(round_out), _ptr(mask_out), _ptr(mask_in), _ptr(colsum), mask_scale)
     call('pa_gemm_tf32', C.byref(g), _stream())
     return c
 
@@ -595,6 +597,60 @@ class Linear(Function):
         return dx, dW, db, None, None, None, None, None
 
 
+class FFN(Function):
+    """out = W2 . dropout_p(relu(W1 x + b1))  (torch transformer.py `_ff_block`; linear2's bias is folded into the following
+    residual+LayerNorm kernel) as ONE autograd node on the TF32 tensor cores, so that the activation's backward never makes
+    its own pass over the [tokens, ff] gradient: the FFN1 GEMM epilogue leaves one bit per hidden unit (active and kept),
+    and the epilogue of linear2's dX GEMM applies it (x 1/(1-p)), rounds, and accumulates the column sums = db1.
+    x must be TF32-rounded; W1_r / W2_r are the rounded shadows of W1 / W2."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W1_r, W2, W2_r, p_drop):
+        _require_cuda(x, W1, W2)
+        K, ff, d_out = W1.shape[1], W1.shape[0], W2.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        h = torch.empty(M, ff, device=x.device, dtype=torch.float32)
+        mask = torch.empty(M, ff // 32, device=x.device, dtype=torch.int32)
+        seed, off = RNG.next() if p_drop > 0 else (0, 0)
+        gemm_tf32(x2, W1_r, h, M, ff, K, lda=K, ldb=W1_r.stride(0), ldc=ff, bias=b1, relu=True, p_drop=p_drop, seed=seed, off=off,
+                  round_out=True, mask_out=mask)
+        out = torch.empty(M, d_out, device=x.device, dtype=torch.float32)
+        gemm_tf32(h, W2_r, out, M, d_out, ff, lda=ff, ldb=W2_r.stride(0), ldc=d_out)
+        ctx.save_for_backward(x2, h, mask, W1_r, W2_r)
+        ctx.cfg = (p_drop, x.shape)
+        return out.view(*x.shape[:-1], d_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x2, h, mask, W1_r, W2_r = ctx.saved_tensors
+        p_drop, xshape = ctx.cfg
+        M, K = x2.shape
+        ff, d_out = W1_r.shape[0], W2_r.shape[0]
+        dy = dout.reshape(M, d_out)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        dev = dy.device
+        # dh = dy W2, masked by the activation plane, rounded (it only feeds tensor-core operands); db1 = its column sums
+        dh = torch.empty(M, ff, device=dev, dtype=torch.float32)
+        db1 = _zeros((ff,), dev)
+        gemm_tf32(dy, W2_r, dh, M, ff, d_out, lda=d_out, ldb=W2_r.stride(0), ldc=ff, b_mn=True, round_out=True,
+                  mask_in=mask, mask_scale=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0, colsum=db1)
+        kb = (M + 31) // 32
+        dW2 = _zeros((d_out, ff), dev)
+        gemm_tf32(dy, h, dW2, d_out, ff, M, lda=d_out, ldb=ff, ldc=ff, a_mn=True, b_mn=True,
+                  split_k=_split_k(((d_out + 127) // 128) * ((ff + 255) // 256), kb), accumulate=True)
+        dx = torch.empty(M, K, device=dev, dtype=torch.float32)
+        gemm_tf32(dh, W1_r, dx, M, K, ff, lda=ff, ldb=W1_r.stride(0), ldc=K, b_mn=True)
+        dW1 = _zeros((ff, K), dev)
+        gemm_tf32(dh, x2, dW1, ff, K, M, lda=ff, ldb=K, ldc=K, a_mn=True, b_mn=True,
+                  split_k=_split_k(((ff + 127) // 128) * ((K + 255) // 256), kb), accumulate=True)
+        return dx.view(xshape), dW1, db1, None, dW2, None, None
+
+
 class PointerScores(Function):
     """Raw pointer scores lp[b] = pf[b] h[b]^T (ref models.py:149; the 1/d and the masking live in the
     distribution kernel) as one batched tcgen05 TF32 GEMM; backward = two batched GEMMs with MN-major operands:
@@ -633,6 +689,7 @@ def pointer_scores(pf, h, tf32):
 
 
 GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
+FFN_FUSED = os.environ.get('PLANK_B200_FFN_FUSED', '1') == '1'        # A/B switch for ops.FFN
 
 
 def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True):

@@ -97,7 +97,7 @@ def test_ctypes_struct_layouts_match_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     probes = [('pa_attn_fwd_args', _lib.AttnFwdArgs, ['q', 'ldq', 'B', 'scale', 'seed', 'impl', 'drop_rows', 'kv_len']),
               ('pa_attn_bwd_args', _lib.AttnBwdArgs, ['q', 'd_o', 'delta', 'lddq', 'kpm', 'scale', 'seed', 'dbias', 'kv_len']),
-              ('pa_gemm_args', _lib.GemmArgs, ['a', 'b', 'c', 'bias', 'seed', 'alpha', 'batch', 'a_batch_rows', 'split_k', 'round_out']),
+              ('pa_gemm_args', _lib.GemmArgs, ['a', 'b', 'c', 'bias', 'seed', 'alpha', 'batch', 'a_batch_rows', 'split_k', 'round_out', 'mask_out', 'colsum', 'mask_scale']),
               ('pa_decode_layer', _lib.DecodeLayer, ['w_sqkv', 'g1', 'w_f2', 'self_k', 'cross_kv']),
               ('pa_decode_fused_args', _lib.DecodeFusedArgs, ['B', 'end_token', 'layer_eps', 'layers', 'gf', 'kpm', 'part', 'part_bytes',
                                                               'hfin', 'first_end', 'state', 'chains', 'profile'])]

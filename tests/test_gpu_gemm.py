@@ -214,3 +214,35 @@ def test_linear_x3_is_fp32_class(M, N, K):
     print(f'x3 {M}x{N}x{K}: rel err vs fp64 {e:.2e} (torch fp32 matmul: {e32:.2e})')
     assert e < 1e-5 and e < 10 * e32 + 1e-7        # measured 5e-6 (fp32 matmul 8e-7, plain TF32 5e-4): tensor-core accumulation order
     assert torch.equal(y_rows, y[:, N // 2:])
+
+
+@pytest.mark.parametrize('M,d,ff,p', [(1196, 512, 1024, 0.2), (300, 128, 256, 0.0), (4096, 256, 1024, 0.1)])
+def test_fused_ffn_matches_the_two_linears(M, d, ff, p):
+    """ops.FFN (activation backward fused into the epilogues: relu/dropout bit plane out of the FFN1 GEMM, masked dX + bias
+    column sums in linear2's dX GEMM) against the unfused composition with the same RNG state."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = ops_round(torch.randn(M, d, generator=g)).cuda()
+    W1 = (torch.randn(ff, d, generator=g) / d ** 0.5).cuda()
+    b1 = torch.randn(ff, generator=g).cuda()
+    W2 = (torch.randn(d, ff, generator=g) / ff ** 0.5).cuda()
+    w = torch.randn(M, d, generator=g).cuda()
+    res = []
+    for fused in (True, False):
+        xs, p1, pb, p2 = [t.clone().requires_grad_(True) for t in (x, W1, b1, W2)]
+        ops.begin_step()
+        torch.manual_seed(123)
+        if fused:
+            out = ops.FFN.apply(xs, p1, pb, ops.tf32_weight(p1), p2, ops.tf32_weight(p2), p)
+        else:
+            h = ops.linear(xs, p1, pb, relu=True, p_drop=p, tf32=True, round_out=True)
+            out = ops.linear(h, p2, None, tf32=True, round_dx=True)
+        (out * w).sum().backward()
+        res.append((out.detach(), xs.grad, p1.grad, pb.grad, p2.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b, name in zip(res[0][1:], res[1][1:], ('dx', 'dW1', 'db1', 'dW2')):
+        assert rel_err(a.cpu(), b.cpu()) < 2e-5, name
+
+
+def ops_round(t):
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
