@@ -43,6 +43,9 @@ namespace {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 32;         // 32 tf32 = 128 B = one swizzle row
 constexpr int UK = 8;          // K per tcgen05.mma.kind::tf32
+#ifndef PA_GEMM_STORE_SLOTS
+#define PA_GEMM_STORE_SLOTS 2
+#endif
 constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct GemmParams {
@@ -66,11 +69,13 @@ struct GemmParams {
 // HALF of the B tile (BN/2 rows), the tensor cores of the two SMs exchange the halves -- a third less shared-memory traffic
 // per flop than the single-SM form (fp32 operands make these GEMMs smem-bandwidth bound) and room for deeper pipelines.
 template <int BN, bool TWO = false> struct Cfg {
-  static constexpr int kStages = TWO ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6);
+  static constexpr int kSlots = PA_GEMM_STORE_SLOTS;     // staging tiles per epilogue warp (TMA-store epilogue)
+  static constexpr int kStages = kSlots > 1 ? (TWO ? (BN == 256 ? 5 : 6) : (BN == 256 ? 3 : 5))
+                                            : (TWO ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6));
   static constexpr int kABytes = BM * BK * 4;           // 16 KB
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageOut = 8 * 32 * 128;        // per epilogue warp: one 32x32 fp32 tile, 128B-swizzled
+  static constexpr int kStageOut = 8 * kSlots * 32 * 128;   // per epilogue warp: kSlots 32x32 fp32 tiles, 128B-swizzled
   static constexpr int kSmem = kStages * kStageBytes + kStageOut + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BN;              // double-buffered accumulator
   static_assert(kSmem <= 232448, "dynamic shared memory budget of one CTA");
@@ -86,7 +91,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   using C = Cfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [8 warps][32 rows][128 B]
+  uint8_t* out_stage = smem + C::kStages * C::kStageBytes;                 // [8 warps][kSlots][32 rows][128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + C::kStageOut);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full = empty_bar + C::kStages;
@@ -257,6 +262,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                  // which of the quarter's two warps: takes chunks half, half+2, ...
     int acc = 0; uint32_t acc_phase = 0;
+    int slot = 0;
     const uint32_t thr = drop_threshold(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     GTRACE_DECL(warp == 2 && lane == 0);
@@ -279,6 +285,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       float* crow = p.c + (int64_t)b * p.c_batch_stride + (int64_t)row * p.ldc;
 #pragma unroll 1
       for (int c0 = half * 32; c0 < ((p.debug & 1) ? 0 : BN); c0 += 64) {
+        // Every flag below is warp-uniform and every stage is its own 32-wide loop of INDEPENDENT operations: with two
+        // epilogue warps per scheduler the per-element form (load bias -> add -> relu -> ... one element after the other)
+        // was a dependent chain of ~400 instructions per chunk and, not the stores, what made the epilogue longer than a
+        // K = 512 mainloop (ablation: scripts/ablate_gemm.py).
         uint32_t r[32];
         if (!(p.debug & 4)) {
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
@@ -288,133 +298,127 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int i = 0; i < 32; ++i) r[i] = i;
         }
         const int col0 = nt * BN + c0;
-        if (p.tma_store) {
-          if (kb1 > kb0 && col0 < p.N) {        // warp-uniform
-            uint8_t* my_stage = out_stage + (warp - 2) * (32 * 128);
-            const bool direct = p.epi_direct && !p.accumulate;
-            // (two alternating slots per warp were tried: the ~2700-cycle wait moves into the TMA queue, no gain)
-            if (!direct && lane == 0 && !(p.debug & 2)) tc::tma_store_wait_read();       // previous chunk's smem tile has been read out
-            __syncwarp();
-            GTRACE(2, 2);
+        if (col0 >= p.N || kb1 <= kb0) continue;          // warp-uniform
+        float x[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int col = col0 + j;
-              float v[4];
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]);
+        if (p.alpha != 1.f) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x = __uint_as_float(r[j + e]) * p.alpha;
-                if (p.bias != nullptr) x += tc::ld_shared_f32(bias_u32 + 4 * (c0 + j + e));
-                if (p.relu) x = fmaxf(x, 0.f);
-                v[e] = x;
-              }
-              if (p.p_drop > 0.f) {
-                uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col) >> 2), p.offset);
-                v[0] = rn.x >= thr ? v[0] * ks : 0.f; v[1] = rn.y >= thr ? v[1] * ks : 0.f;
-                v[2] = rn.z >= thr ? v[2] * ks : 0.f; v[3] = rn.w >= thr ? v[3] * ks : 0.f;
-              }
-              if (p.round_out) {
+          for (int i = 0; i < 32; ++i) x[i] *= p.alpha;
+        }
+        if (p.bias != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = tf32_rn(v[e]);
-              }
-              // 128B swizzle: 16-byte chunk index XOR (row & 7) -- the layout the C tensor map expects
-              tc::st_shared_v4(tc::smem_u32(my_stage) + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4), v[0], v[1], v[2], v[3]);
-            }
-            if (direct) {
-              // read the tile back row-wise: 8 lanes cover one 128-byte row segment (conflict-free: a quarter warp = one
-              // swizzled row), 4 rows per instruction -> fully coalesced 16-byte global stores, nothing queued behind the
-              // producer's TMA loads and no async-proxy fence
-              __syncwarp();
-              const int rr = lane >> 3, cc = lane & 7;
-              const int64_t grow0 = (int64_t)b * p.M + mt * BM + q * 32;
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + rr;
-                const float4 o = tc::ld_shared_v4(tc::smem_u32(my_stage) + r * 128 + ((cc ^ (r & 7)) << 4));
-                const int col = col0 + cc * 4;
-                if (mt * BM + q * 32 + r < p.M && !(p.debug & 2)) {
-                  float* dst = p.c + (grow0 + r) * p.ldc + col;        // batched C is [batch*M, N] here (tma_store precondition)
-                  if (col + 3 < p.N) *reinterpret_cast<float4*>(dst) = o;
-                  else {
-                    if (col < p.N) dst[0] = o.x;
-                    if (col + 1 < p.N) dst[1] = o.y;
-                    if (col + 2 < p.N) dst[2] = o.z;
-                  }
-                }
-              }
-              continue;
-            }
-            if (!(p.debug & 16)) tc::fence_proxy_async();      // (debug bit 16: timing experiment without the proxy fence)
-            __syncwarp();
-            if (lane == 0 && !(p.debug & 2)) {
-              const int y = b * p.M + mt * BM + q * 32;
-              if (p.accumulate) tc::tma_reduce_add_2d(&tma_c, my_stage, col0, y);
-              else tc::tma_store_2d(&tma_c, my_stage, col0, y);
-              tc::tma_store_commit();
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = tc::ld_shared_v4(bias_u32 + 4 * (c0 + 4 * j));      // broadcast: all lanes read the same 16 bytes
+            x[4 * j] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
           }
-        } else if (col0 < p.N && (row_ok || p.colsum != nullptr)) {
-          // register-direct stores: every lane owns one output row and writes its 32 consecutive columns itself -- NO
-          // shared-memory traffic at all (the mainloop already runs at the smem bandwidth; a staged epilogue adds a write
-          // and a read of the whole tile to it).  256-bit stores = whole 32-byte sectors per lane.
-          // Fused FFN activation backward: a lane's 32 columns are exactly one word of the relu/dropout bit plane.
-          const int mask_ld = p.N >> 5;
-          const uint32_t min_w = (p.mask_in != nullptr && row_ok) ? __ldg(p.mask_in + (int64_t)row * mask_ld + (col0 >> 5)) : 0u;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+        }
+        const int mask_ld = p.N >> 5;
+        if (p.mask_in != nullptr) {       // fused FFN activation backward: a lane's 32 columns are one word of the relu/dropout bit plane
+          const uint32_t min_w = row_ok ? __ldg(p.mask_in + (int64_t)row * mask_ld + (col0 >> 5)) : 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = ((min_w >> i) & 1u) ? x[i] * p.mask_scale : 0.f;
+        }
+        if (p.p_drop > 0.f) {
+          // same element -> (counter, lane) mapping as relu_dropout_fwd_kernel: float4 index of [M,N]
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col0 + 4 * j) >> 2), p.offset);
+            x[4 * j + 0] = rn.x >= thr ? x[4 * j + 0] * ks : 0.f; x[4 * j + 1] = rn.y >= thr ? x[4 * j + 1] * ks : 0.f;
+            x[4 * j + 2] = rn.z >= thr ? x[4 * j + 2] * ks : 0.f; x[4 * j + 3] = rn.w >= thr ? x[4 * j + 3] * ks : 0.f;
+          }
+        }
+        if (p.mask_out != nullptr && row_ok) {
           uint32_t mout_w = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mout_w |= (uint32_t)(x[i] > 0.f) << i;
+          p.mask_out[(int64_t)row * mask_ld + (col0 >> 5)] = mout_w;
+        }
+        if (p.colsum != nullptr) {        // column sums over the warp's 32 rows (bias gradient) take the UNROUNDED values
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = col0 + j;
-            float v[8];
+          for (int i = 0; i < 32; ++i) f[i] = (row_ok && col0 + i < p.N) ? x[i] : 0.f;
+          const float cs = warp_colsum32(f, lane);
+          if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
+        }
+        if (p.round_out) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(r[j + e]) * p.alpha;
-              if (p.bias != nullptr) x += tc::ld_shared_f32(bias_u32 + 4 * (c0 + j + e));
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (p.mask_in != nullptr) x = ((min_w >> (j + e)) & 1u) ? x * p.mask_scale : 0.f;
-              v[e] = x;
-            }
-            if (p.p_drop > 0.f) {
-              // same element -> (counter, lane) mapping as relu_dropout_fwd_kernel: float4 index of [M,N]
+          for (int i = 0; i < 32; ++i) x[i] = tf32_rn(x[i]);
+        }
+        if (p.tma_store) {
+          uint8_t* my_stage = out_stage + ((warp - 2) * C::kSlots + slot) * (32 * 128);
+          if (C::kSlots > 1) slot ^= 1;
+          const bool direct = p.epi_direct && !p.accumulate;
+          // the smem tile written kSlots chunks ago has been read out by its TMA store
+          if (!direct && lane == 0 && !(p.debug & 2)) { if (C::kSlots > 1) tc::tma_store_wait_read1(); else tc::tma_store_wait_read(); }
+          __syncwarp();
+          GTRACE(2, 2);
+          // 128B swizzle: 16-byte chunk index XOR (row & 7) -- the layout the C tensor map expects
 #pragma unroll
-              for (int h4 = 0; h4 < 2; ++h4) {
-                uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col + 4 * h4) >> 2), p.offset);
-                v[4 * h4 + 0] = rn.x >= thr ? v[4 * h4 + 0] * ks : 0.f; v[4 * h4 + 1] = rn.y >= thr ? v[4 * h4 + 1] * ks : 0.f;
-                v[4 * h4 + 2] = rn.z >= thr ? v[4 * h4 + 2] * ks : 0.f; v[4 * h4 + 3] = rn.w >= thr ? v[4 * h4 + 3] * ks : 0.f;
+          for (int j = 0; j < 8; ++j)
+            tc::st_shared_v4(tc::smem_u32(my_stage) + lane * 128 + ((j ^ (lane & 7)) << 4), x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          if (direct) {
+            // read the tile back row-wise: 8 lanes cover one 128-byte row segment (conflict-free: a quarter warp = one
+            // swizzled row), 4 rows per instruction -> fully coalesced 16-byte global stores, nothing queued behind the
+            // producer's TMA loads and no async-proxy fence
+            __syncwarp();
+            const int rr = lane >> 3, cc = lane & 7;
+            const int64_t grow0 = (int64_t)b * p.M + mt * BM + q * 32;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r2 = it * 4 + rr;
+              const float4 o = tc::ld_shared_v4(tc::smem_u32(my_stage) + r2 * 128 + ((cc ^ (r2 & 7)) << 4));
+              const int col = col0 + cc * 4;
+              if (mt * BM + q * 32 + r2 < p.M && !(p.debug & 2)) {
+                float* dst = p.c + (grow0 + r2) * p.ldc + col;        // batched C is [batch*M, N] here (tma_store precondition)
+                if (col + 3 < p.N) *reinterpret_cast<float4*>(dst) = o;
+                else {
+                  if (col < p.N) dst[0] = o.x;
+                  if (col + 1 < p.N) dst[1] = o.y;
+                  if (col + 2 < p.N) dst[2] = o.z;
+                }
               }
             }
-            if (p.round_out) {
+            continue;
+          }
+          if (!(p.debug & 16)) tc::fence_proxy_async();      // (debug bit 16: timing experiment without the proxy fence)
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 2)) {
+            const int y = b * p.M + mt * BM + q * 32;
+            if (p.accumulate) tc::tma_reduce_add_2d(&tma_c, my_stage, col0, y);
+            else tc::tma_store_2d(&tma_c, my_stage, col0, y);
+            tc::tma_store_commit();
+          }
+        } else if (row_ok && !(p.debug & 2)) {
+          // register-direct stores: every lane owns one output row and writes its 32 consecutive columns itself -- no
+          // shared-memory traffic at all.  256-bit stores = whole 32-byte sectors per lane.
+          if (p.wide8 && !p.accumulate && col0 + 32 <= p.N) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = tf32_rn(v[e]);
-            }
+            for (int j = 0; j < 4; ++j)
+              st_global_v8(crow + col0 + 8 * j, make_float4(x[8 * j], x[8 * j + 1], x[8 * j + 2], x[8 * j + 3]),
+                           make_float4(x[8 * j + 4], x[8 * j + 5], x[8 * j + 6], x[8 * j + 7]));
+          } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              f[j + e] = (row_ok && col + e < p.N) ? v[e] : 0.f;
-              mout_w |= (uint32_t)(v[e] > 0.f) << (j + e);
-            }
-            if (!row_ok || col >= p.N) continue;
-            if (p.wide8 && !p.accumulate && col + 7 < p.N) {
-              st_global_v8(crow + col, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
-            } else {
+            for (int j = 0; j < 8; ++j) {
+              const int c4 = col0 + 4 * j;
+              if (c4 + 3 < p.N && ((p.ldc & 3) == 0)) {
+                const float4 o = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + c4), o);
+                else *reinterpret_cast<float4*>(crow + c4) = o;
+              } else {
 #pragma unroll
-              for (int h4 = 0; h4 < 2; ++h4) {
-                const int c4 = col + 4 * h4;
-                if (c4 + 3 < p.N && ((p.ldc & 3) == 0)) {
-                  float4 o = make_float4(v[4 * h4], v[4 * h4 + 1], v[4 * h4 + 2], v[4 * h4 + 3]);
-                  if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(crow + c4), o);
-                  else *reinterpret_cast<float4*>(crow + c4) = o;
-                } else {
-                  for (int e = 0; e < 4 && c4 + e < p.N; ++e) {
-                    if (p.accumulate) atomicAdd(crow + c4 + e, v[4 * h4 + e]);
-                    else crow[c4 + e] = v[4 * h4 + e];
+                for (int e = 0; e < 4; ++e) {
+                  if (c4 + e < p.N) {
+                    if (p.accumulate) atomicAdd(crow + c4 + e, x[4 * j + e]);
+                    else crow[c4 + e] = x[4 * j + e];
                   }
                 }
               }
             }
-          }
-          if (p.mask_out != nullptr && row_ok) p.mask_out[(int64_t)row * mask_ld + (col0 >> 5)] = mout_w;
-          if (p.colsum != nullptr) {          // warp-uniform: all 32 lanes are here; column sums over the warp's 32 rows
-            const float cs = warp_colsum32(f, lane);
-            if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
           }
         }
       }
@@ -475,9 +479,12 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   // TMA-store epilogue: C seen as [batch*M, N] rows of pitch ldc (clipped at the bounds by the TMA)
   p.tma_store = (a.ldc % 4 == 0) && (((uintptr_t)a.c & 15) == 0) &&
                 (p.batch == 1 || (a.M % BM == 0 && a.c_batch_stride == (int64_t)a.M * a.ldc));
-  // PLANK_B200_GEMM_EPI: 0 = staged smem tile + TMA store, 1 = staged tile + coalesced st.global (measured slower than 0:
-  // 120 vs 107 us on the QKV projection), 2 = register-direct 256-bit stores, no smem traffic (split-K keeps TMA reduce-add)
-  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 2 : atoi(e); }
+  // PLANK_B200_GEMM_EPI: 0 (default) = staged smem tile + TMA store, 1 = staged tile + coalesced st.global, 2 = register-direct
+  // 256-bit stores (split-K keeps the TMA reduce-add).  The fp32-operand mainloop already keeps the shared-memory port busy
+  // (64 KB written + read per 512-cycle k-block), so what an epilogue costs is its L1/smem datapath cycles per 128 KB tile:
+  // ~2k for 0 (conflict-free st.shared + full-width TMA read), ~4k for 2 (every 256-bit store touches 32 different lines);
+  // measured on the QKV projection (32768 x 1536 x 512, burst clocks): mainloop only 66.6 us, 0: 93.4, 1: 98.7, 2: 99.5.
+  { const char* e = getenv("PLANK_B200_GEMM_EPI"); p.epi_direct = e == nullptr ? 0 : atoi(e); }
   p.wide8 = (a.ldc % 8 == 0) && (((uintptr_t)a.c & 31) == 0) && (a.c_batch_stride % 8 == 0);
   if (p.epi_direct == 2 && !p.accumulate) p.tma_store = 0;
   p.mask_out = a.mask_out; p.mask_in = a.mask_in; p.colsum = a.colsum; p.mask_scale = a.mask_scale;
@@ -493,6 +500,7 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   if ((rc = pa_set_max_smem(kern, C::kSmem, attr))) return rc;
   int tiles = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.split_k * p.batch;      // cluster steps
   int grid = (tiles * CL < pa_num_sms() ? tiles * CL : (pa_num_sms() / CL) * CL);
+  { const char* g = getenv("PLANK_B200_GEMM_GRID"); if (g != nullptr && atoi(g) > 0 && atoi(g) < grid) grid = atoi(g) / CL * CL; }   // experiments: fewer SMs
   if constexpr (CL == 1) {
     kern<<<grid, kThreads, C::kSmem, st>>>(ta, tb, tc_map, p);
   } else {
