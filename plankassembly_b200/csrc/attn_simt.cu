@@ -109,13 +109,11 @@ struct DropCtx {
   bool on;
 };
 
-// keep-mask for the 4 consecutive keys kj0..kj0+3 (kj0 % 4 == 0) of query row `row_global` (= (b*H+h)*Lq + qi):
-// Philox counter = row_global * ceil(Lk/8) + k/8; key k uses 16 bits: word (k%8)/2, half k%2 (same rule as dropmask.cu)
-__device__ __forceinline__ void drop_mask4(const DropCtx& D, int64_t row_global, int Lk8, int kj0, float m[4]) {
-  const uint4 r = philox4x32(D.seed, (uint64_t)(row_global * Lk8 + (kj0 >> 3)), D.offset);
-  const uint32_t w0 = (kj0 & 4) ? r.z : r.x, w1 = (kj0 & 4) ? r.w : r.y;
-  m[0] = (w0 & 0xffffu) >= D.thr ? D.ks : 0.f; m[1] = (w0 >> 16) >= D.thr ? D.ks : 0.f;
-  m[2] = (w1 & 0xffffu) >= D.thr ? D.ks : 0.f; m[3] = (w1 >> 16) >= D.thr ? D.ks : 0.f;
+// keep-mask for the 4 consecutive keys kj0..kj0+3 (kj0 % 4 == 0) of query row `row_global` (= (b*H+h)*Lq + qi): bits of the
+// row's keep word for key word kj0/32, recomputed here by the same rule as the bit planes of dropmask.cu (drop_keep_word)
+__device__ __forceinline__ void drop_mask4(const DropCtx& D, int64_t row_global, int LkW, int kj0, float m[4]) {
+  const uint32_t w = drop_keep_word(D.seed, D.offset, row_global, LkW, kj0 >> 5, 65536u - D.thr) >> (kj0 & 31);
+  m[0] = (w & 1u) ? D.ks : 0.f; m[1] = (w & 2u) ? D.ks : 0.f; m[2] = (w & 4u) ? D.ks : 0.f; m[3] = (w & 8u) ? D.ks : 0.f;
 }
 
 template <int DH>
@@ -133,7 +131,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_simt_kernel(pa_attn_fwd_args A) {
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
   DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
+  const int Lk4 = (A.Lk + 31) / 32;    // keep words (32 keys) per row
 
   load_tile<DH, false>(Qs, qp, A.ldq, q0, A.Lq);
   float m_run[4], l_run[4], o[4][W];
@@ -290,7 +288,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_dkdv_simt_kernel(pa_attn_bwd_args
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
   DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
+  const int Lk4 = (A.Lk + 31) / 32;    // keep words (32 keys) per row
   load_tile<DH, true>(Ks, kp, A.ldk, k0, A.Lk);
   load_tile<DH, true>(Vs, vp, A.ldv, k0, A.Lk);
   if (threadIdx.x < BN) {
@@ -348,7 +346,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_dq_simt_kernel(pa_attn_bwd_args A
   const float* kp = A.k + (int64_t)b * A.Lk * A.ldk + h * DH;
   const float* vp = A.v + (int64_t)b * A.Lk * A.ldv + h * DH;
   DropCtx D{A.seed, A.offset, drop_threshold16(A.p_drop), A.p_drop > 0.f ? 1.f / (1.f - A.p_drop) : 1.f, A.p_drop > 0.f};
-  const int Lk4 = (A.Lk + 7) / 8;      // Philox groups (8 keys) per row
+  const int Lk4 = (A.Lk + 31) / 32;    // keep words (32 keys) per row
   load_tile<DH, false>(Qs, qp, A.ldq, q0, A.Lq);
   load_tile<DH, false>(dOs, dop, A.ldo, q0, A.Lq);
   if (threadIdx.x < BM) {

@@ -119,11 +119,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // Philox4x32-10 counter-based RNG: dropout masks are a pure function of (seed, offset, element
 // index), so backward kernels regenerate the forward mask instead of storing it.
 // ---------------------------------------------------------------------------------------------
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
@@ -132,8 +133,29 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Attention-probability dropout draws 16 random bits per score (one Philox4x32-10 call covers 8 consecutive keys):
-// keep iff half-word >= p * 2^16, i.e. the drop probability is p rounded down to a multiple of 2^-16.
+// Attention-probability dropout, bit-sliced: the keep bits of (query row, 32 consecutive keys) are ONE word, built from 16
+// random words (4 calls of Philox4x32-7, the Crush-resistant round count of the Random123 paper; the 10-round default only adds
+// margin and this kernel is pure ALU) by folding them over the binary digits of the keep probability q = keep16 / 2^16, least
+// significant digit first:  W <- digit ? (W | r) : (W & r).  Every bit of W is then 1 with probability exactly q,
+// independently of the others -- the same distribution as comparing 16 random bits per score with a threshold, for 16 logic
+// operations per 32 scores instead of ~100.  `row_pitch_words` = ceil(Lk / 32).  Shared by dropmask.cu (the bit planes the
+// tensor-core kernels read) and attn_simt.cu (which recomputes single words).
+__device__ __forceinline__ uint32_t drop_keep_word(uint64_t seed, uint64_t offset, int64_t row_global, int row_pitch_words, int kw, uint32_t keep16) {
+  if (keep16 >= 65536u) return 0xffffffffu;
+  uint32_t W = 0u;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 r = philox4x32<7>(seed, (uint64_t)((row_global * row_pitch_words + kw) * 4 + g), offset);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) W = ((keep16 >> (4 * g + e)) & 1u) ? (W | w[e]) : (W & w[e]);
+  }
+  return W;
+}
+
+// Dropout probabilities are quantised to 16 bits: residual-row dropout (LayerNorm kernels) draws 16 random bits per element
+// and keeps iff half-word >= p * 2^16; the attention bit planes use keep16 = 2^16 - threshold (drop_keep_word above).  Either
+// way the drop probability is p rounded down to a multiple of 2^-16.
 __host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
   double t = (double)p * 65536.0;
   return t >= 65535.0 ? 0xFFFFu : (uint32_t)t;

@@ -1,8 +1,8 @@
 // Attention-probability dropout masks as bit planes, generated once per attention call by the whole chip.
 // Inside the tensor-core attention kernels only 4 warps per SM do elementwise work, and Philox4x32-10 was
 // ~2/3 of their instructions (and was recomputed in the forward, dQ and dK/dV kernels).  Here every thread
-// owns (query q, 32 consecutive keys): 4 Philox calls (16 random bits per key) -> one row-major mask word; 32 ballots transpose the
-// 32x32 block so that the key-stationary backward can read its (key, 32 queries) word directly.
+// owns (query q, 32 consecutive keys): 4 Philox calls folded bit-sliced into one row-major mask word (drop_keep_word, common.cuh);
+// a shuffle bit-matrix transpose of the 32x32 block gives the key-stationary backward its (key, 32 queries) word.
 #include "common.cuh"
 
 namespace {
@@ -15,21 +15,10 @@ __global__ void __launch_bounds__(128) dropout_mask_kernel(uint32_t* __restrict_
   const int bh = blockIdx.z;
   if (kw >= LkW) return;
   const int q = qb * 32 + lane;
-  const int Lk8 = (Lk + 7) / 8;
   uint32_t word = 0;
   if (q < Lq) {
     const int64_t rg = (int64_t)bh * Lq + q;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int k8 = kw * 4 + g;
-      if (k8 < Lk8) {
-        const uint4 r = philox4x32(seed, (uint64_t)(rg * Lk8 + k8), offset);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          word |= (uint32_t)((w[e] & 0xffffu) >= thr) << (8 * g + 2 * e) | (uint32_t)((w[e] >> 16) >= thr) << (8 * g + 2 * e + 1);
-      }
-    }
+    word = drop_keep_word(seed, offset, rg, LkW, kw, 65536u - thr);
     rows[rg * LkW + kw] = word;
   }
   if (cols != nullptr) {

@@ -6,8 +6,37 @@
 // Algorithmic bytes per row: fwd reads 2*d*4 (x, a) and writes 2*d*4 (y, s) + 8; bwd reads 2*d*4
 // (dy, s) and writes up to 2*d*4 (dx, da).
 #include "common.cuh"
+#include <stdlib.h>
 
 constexpr int kLnWarps = 4;
+// The row-per-warp kernels issue a row's loads, reduce, store, and only then touch the next row: with few resident warps
+// (the backward needs 148 registers: 12 warps per SM) too few bytes are in flight to cover the DRAM latency (ncu: 3.0 TB/s).
+// Each warp therefore pulls the rows it will process NEXT into L2 while it works on the current one (no registers, no smem).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int NV>
+__device__ __forceinline__ void prefetch_rows(int lane, int64_t row, const float4* t0, const float4* t1, const float4* t2) {
+  constexpr int kLines = NV * 4;                       // 128-byte lines per row (d * 4 / 128)
+  const float4* ts[3] = {t0, t1, t2};
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (ts[t] == nullptr) continue;
+    for (int l = lane; l < kLines; l += 32) prefetch_l2(reinterpret_cast<const char*>(ts[t] + row * (NV * 32)) + l * 128);
+  }
+}
+static inline int ln_debug() {
+  static const int v = [] { const char* e = getenv("PLANK_B200_LN_DEBUG"); return e ? atoi(e) : 0; }();
+  return v;
+}
+// Measured on the encoder shape (32768 x 512, scripts/bench_ln.py): backward 89 -> 69 us with one row of look-ahead (3.0 -> 3.9 TB/s);
+// the forward (56 registers, 32 warps per SM, 5.4 TB/s = torch's copy at this size) gets slower with it (49 -> 56 us): off there.
+static inline int ln_prefetch_depth() {
+  static const int v = [] { const char* e = getenv("PLANK_B200_LN_PREFETCH"); return e ? atoi(e) : 1; }();
+  return v;
+}
+static inline int ln_prefetch_fwd() {
+  static const int v = [] { const char* e = getenv("PLANK_B200_LN_PREFETCH_FWD"); return e ? atoi(e) : 0; }();
+  return v;
+}
 // Blocks of 4 warps per SM for the row-per-warp LayerNorm kernels.  The ncu capture of round 2 showed add_ln_fwd at 3.4 TB/s
 // with 24 % of the warp slots occupied (4 blocks per SM: too few rows in flight to cover the HBM latency, the loads of a
 // warp's next row are only issued after its current row is stored), hence 8 (measured per step: 4 -> 22.71 ms, 8 -> 21.90, 16 -> 21.95, 32 -> 22.06); PLANK_B200_LN_BLOCKS_PER_SM overrides.
@@ -29,13 +58,16 @@ template <int NV>  // float4 per lane; d = NV*128
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ a, const float4* __restrict__ abias,
                                                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float eps, float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
-                                                                     float4* __restrict__ y, float4* __restrict__ y_r, float4* __restrict__ s_out, float2* __restrict__ stats) {
+                                                                     float4* __restrict__ y, float4* __restrict__ y_r, float4* __restrict__ s_out, float2* __restrict__ stats,
+                                                                     int prefetch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32;
   const float inv_d = 1.f / (float)(NV * 128);
   const uint32_t thr = drop_threshold16(p_drop);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
+    const int64_t ahead = row + (int64_t)prefetch * gridDim.x * kLnWarps;
+    if (prefetch > 0 && ahead < rows) prefetch_rows<NV>(lane, ahead, x, a, nullptr);
     float4 v[NV];
     float sum = 0.f;
     uint4 r = make_uint4(0u, 0u, 0u, 0u);
@@ -89,7 +121,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
                                                                      const float2* __restrict__ stats, const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
                                                                      float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial,
-                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dabias) {
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dabias,
+                                                                     int prefetch, int debug) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = NV * 32, d = NV * 128;
   const float inv_d = 1.f / (float)d;
@@ -99,6 +132,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
 #pragma unroll
   for (int i = 0; i < NV; ++i) dg[i] = db[i] = dab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows; row += (int64_t)gridDim.x * kLnWarps) {
+    const int64_t ahead = row + (int64_t)prefetch * gridDim.x * kLnWarps;
+    if (prefetch > 0 && ahead < rows) prefetch_rows<NV>(lane, ahead, dy, s, dy2);
     const float2 st = __ldg(stats + row);
     float4 g[NV], xh[NV];
     float c1 = 0.f, c2 = 0.f;
@@ -166,7 +201,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4*
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
     float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dabias);
-    atomicAdd(reinterpret_cast<float4*>(dst) + c, acc);
+    if (!(debug & 1)) atomicAdd(reinterpret_cast<float4*>(dst) + c, acc);
   }
 }
 
@@ -187,7 +222,7 @@ extern "C" int pa_add_ln_fwd(const float* x, const float* a, const float* a_bias
 #define LAUNCH(NV)                                                                                                   \
   add_ln_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)x, (const float4*)a, (const float4*)a_bias, (const float4*)gamma, \
                                                          (const float4*)beta, eps, p_drop, seed, offset, rows,          \
-                                                         (float4*)y, (float4*)y_tf32, (float4*)s, (float2*)stats)
+                                                         (float4*)y, (float4*)y_tf32, (float4*)s, (float2*)stats, ln_prefetch_fwd())
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -211,7 +246,7 @@ extern "C" int pa_add_ln_bwd(const float* dy, const float* dy2, const float* s, 
 #define LAUNCH(NV)                                                                                                   \
   add_ln_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const float4*)dy, (const float4*)dy2, (const float4*)s, (const float2*)stats,    \
                                                          (const float4*)gamma, (const float4*)beta, p_drop, seed, offset, rows, (float4*)dx, \
-                                                         (float4*)da, round_da, d_a_bias != nullptr, (float*)partial, dgamma, dbeta, d_a_bias)
+                                                         (float4*)da, round_da, d_a_bias != nullptr, (float*)partial, dgamma, dbeta, d_a_bias, ln_prefetch_depth(), ln_debug())
   switch (d / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;

@@ -4,6 +4,7 @@ the round-to-nearest of P before the P V contraction; tolerance 5e-4 relative (b
 import math
 
 import pytest
+import numpy as np
 import torch
 
 pytestmark = pytest.mark.gpu
@@ -105,6 +106,28 @@ def test_tc_dropout_matches_simt_mask():
     assert torch.equal(o_tc > 0, o_simt > 0)
     assert abs((o_tc > 0).float().mean().item() - (1 - p)) < 2e-2
     assert rel_err(o_tc.cpu(), o_simt.cpu()) < TOL
+
+
+def test_dropout_bit_planes_statistics():
+    """The bit-sliced keep words (common.cuh drop_keep_word: 16 Philox words folded over the binary digits of the keep
+    probability): keep rate = 1 - p to 3 sigma over 8 M scores, neighbouring keys / queries / words uncorrelated, and the
+    column-major plane is the exact transpose of the row-major one."""
+    from plankassembly_b200 import ops
+    BH, Lq, Lk = 8, 1024, 1024
+    for p in (0.2, 0.1, 0.5):
+        rows, cols = ops._drop_masks(BH, 1, Lq, Lk, p, 20221, 7, torch.device('cuda'))
+        r = rows.view(BH, Lq, Lk // 32).cpu().numpy().astype(np.uint32)
+        bits = ((r[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(BH, Lq, Lk).astype(np.float64)     # [bh, q, k]
+        q_keep = 1.0 - int(p * 65536) / 65536.0
+        n = bits.size
+        sigma = (q_keep * (1 - q_keep) / n) ** 0.5
+        assert abs(bits.mean() - q_keep) < 4 * sigma, (p, bits.mean())
+        for a, b in ((bits[:, :, 1:], bits[:, :, :-1]), (bits[:, 1:], bits[:, :-1]), (bits[:, :, 32:], bits[:, :, :-32])):
+            cov = (a * b).mean() - a.mean() * b.mean()
+            assert abs(cov) < 5 * q_keep * (1 - q_keep) / a.size ** 0.5, (p, cov)
+        c = cols.view(BH, Lk, Lq // 32).cpu().numpy().astype(np.uint32)
+        cbits = ((c[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(BH, Lk, Lq)                      # [bh, k, q]
+        assert np.array_equal(cbits.transpose(0, 2, 1), bits.astype(np.uint32))
 
 
 # ------------------------------------------------------------------------------ backward (tcgen05)
