@@ -263,7 +263,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int half = (warp - 2) >> 2;                  // which of the quarter's two warps: takes chunks half, half+2, ...
     int acc = 0; uint32_t acc_phase = 0;
     int slot = 0;
-    const uint32_t thr = drop_threshold(p.p_drop);
+    const uint32_t keep16 = 65536u - drop_threshold16(p.p_drop);
     const float ks = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     GTRACE_DECL(warp == 2 && lane == 0);
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -324,13 +324,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int i = 0; i < 32; ++i) x[i] = ((min_w >> i) & 1u) ? x[i] * p.mask_scale : 0.f;
         }
         if (p.p_drop > 0.f) {
-          // same element -> (counter, lane) mapping as relu_dropout_fwd_kernel: float4 index of [M,N]
+          // a lane's 32 columns take ONE bit-sliced keep word (drop_keep_word, common.cuh: 4 Philox4x32-7 calls) -- the
+          // per-element form cost 8 Philox4x32-10 calls per chunk on the two epilogue warps of a scheduler
+          const uint32_t kw = drop_keep_word(p.seed, p.offset, row, (p.N + 31) >> 5, col0 >> 5, keep16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 rn = philox4x32(p.seed, (uint64_t)(((int64_t)row * p.N + col0 + 4 * j) >> 2), p.offset);
-            x[4 * j + 0] = rn.x >= thr ? x[4 * j + 0] * ks : 0.f; x[4 * j + 1] = rn.y >= thr ? x[4 * j + 1] * ks : 0.f;
-            x[4 * j + 2] = rn.z >= thr ? x[4 * j + 2] * ks : 0.f; x[4 * j + 3] = rn.w >= thr ? x[4 * j + 3] * ks : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) x[i] = ((kw >> i) & 1u) ? x[i] * ks : 0.f;
         }
         if (p.mask_out != nullptr && row_ok) {
           uint32_t mout_w = 0u;

@@ -57,11 +57,15 @@ def test_gemm_relu_dropout_epilogue():
     pos = c > 0
     assert abs(keep[pos].float().mean().item() - (1 - p)) < 1e-2
     assert torch.allclose(c2[keep], c[keep] / (1 - p), rtol=1e-6)
-    # the elementwise kernel must regenerate the very same mask (shared Philox indexing)
-    z = c.clone()
-    from plankassembly_b200._lib import call
-    call('pa_relu_dropout_fwd', z.data_ptr(), z.numel(), p, 7, 3, torch.cuda.current_stream().cuda_stream)
-    assert torch.equal(z > 0, keep)
+    # same (seed, offset) -> same mask; another offset -> another mask.  (The elementwise pa_relu_dropout_fwd of the exact
+    # cuBLAS cross-check path draws its own per-element stream: the epilogue uses one bit-sliced keep word per 32 columns.)
+    c3 = torch.empty(M, N, device='cuda')
+    ops.gemm_tf32(a.cuda(), w.cuda(), c3, M, N, K, lda=K, ldb=K, ldc=N, bias=bias.cuda(), relu=True, p_drop=p, seed=7, off=3)
+    assert torch.equal(c3, c2)
+    ops.gemm_tf32(a.cuda(), w.cuda(), c3, M, N, K, lda=K, ldb=K, ldc=N, bias=bias.cuda(), relu=True, p_drop=p, seed=7, off=4)
+    assert not torch.equal(c3 > 0, keep)
+    both = ((c3 > 0) & keep)[pos].float().mean().item()
+    assert abs(both - (1 - p) ** 2) < 1e-2          # independent streams
 
 
 @pytest.mark.parametrize('M,N,K', [(1196, 512, 1536), (4096, 256, 1024), (256, 1024, 512)])
