@@ -488,7 +488,11 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
 
 // The tensor maps address q/k/v as 2-D [B*L rows, H*dh columns] arrays (row pitch ld) from their own base
 // pointers, so the packed in-projection output [B,L,3d] is consumed in place.
+bool pa_attn_fwd_pp_ok(const pa_attn_fwd_args* a);              // attn_pp.cu: two query tiles per CTA in ping-pong
+int pa_attn_fwd_pp(const pa_attn_fwd_args* a, void* stream);
+
 int pa_attn_fwd_tc(const pa_attn_fwd_args* a, void* stream) {
+  if (pa_attn_fwd_pp_ok(a)) return pa_attn_fwd_pp(a, stream);
   switch (a->dh) {
     case 32: return launch<32>(*a, (cudaStream_t)stream);
     case 64: return launch<64>(*a, (cudaStream_t)stream);

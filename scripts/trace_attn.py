@@ -17,7 +17,8 @@ torch.cuda.synchronize()
 lib = ctypes.CDLL(_lib.LIB_PATH)
 buf = (ctypes.c_ulonglong * (4 * 1024))()
 n = (ctypes.c_int * 4)()
-assert lib.pa_debug_attn_trace(buf, n) == 0
+fn = getattr(lib, os.environ.get('TRACE_FN', 'pa_debug_attn_trace'))
+assert fn(buf, n) == 0
 names = {0: {0: 'q_empty ok', 2: 'k_empty ok', 3: 'v_empty ok'},
          1: {0: 'q_full ok', 1: 'k_full ok', 2: 'QK issued', 3: 'p_full ok', 4: 'o_empty ok', 5: 'v_full ok', 6: 'PV issued'},
          2: {0: 'tile start', 1: 'bar(bias)', 2: 's_full ok', 3: 'S loaded', 4: 'max done', 5: 'exp done', 6: 'P stored', 7: 'p_full arrive',
