@@ -39,6 +39,7 @@ __device__ int g_attn2_trace_n[4];
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
+constexpr int BS = 64;             // keys per softmax step: a K / V tile (BKV keys) is consumed as two halves
 constexpr int kThreads = 384;      // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1 / 2: softmax of tile A / tile B
 // A softmax thread keeps a whole 128-key score row in registers: the warpgroups trade registers at kernel start
 // (setmaxnreg: 4 warps x 80 + 8 warps x 208, within the 12 x 32 x 168 the CTA is launched with); with a uniform 168 the row spilled to local memory.
@@ -73,7 +74,7 @@ struct Params {
   int debug;
 };
 
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const Params p) {
@@ -89,11 +90,12 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* k_empty = bars + 4;           // [2]
   uint64_t* v_full = bars + 6;            // [2]
   uint64_t* v_empty = bars + 8;           // [2]
-  uint64_t* s_full = bars + 10;           // [2 groups]  S_g(j) complete (and with it every earlier MMA: PV_g(j-1))
-  uint64_t* p_full = bars + 12;           // [2 groups]  P_g(j) stored (and O_g rescaled if it had to be)
-  uint64_t* o_final = bars + 14;          // [2 groups]  last PV_g of the item complete
-  uint64_t* o_read = bars + 16;           // [2 groups]  O_g read out: the next item's PV_g(0) may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* s_full = bars + 10;           // [2 groups][2 bufs]  S_g(t) complete
+  uint64_t* p_full = bars + 14;           // [2 groups][2 bufs]  P_g(t) stored (and O_g rescaled if it had to be)
+  uint64_t* o_final = bars + 18;          // [2 groups]  last PV_g of the item complete
+  uint64_t* o_read = bars + 20;           // [2 groups]  O_g read out: the next item's PV_g(0) may overwrite it
+  uint64_t* pv_done = bars + 22;          // [2 groups]  PV_g(t) complete (waited for only before a rescale of O_g)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -102,8 +104,9 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1);
       tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 1);
-      tc::mbar_init(s_full + s, 1); tc::mbar_init(p_full + s, 4);
-      tc::mbar_init(o_final + s, 1); tc::mbar_init(o_read + s, 4);
+      tc::mbar_init(s_full + 2 * s, 1); tc::mbar_init(s_full + 2 * s + 1, 1);
+      tc::mbar_init(p_full + 2 * s, 4); tc::mbar_init(p_full + 2 * s + 1, 4);
+      tc::mbar_init(o_final + s, 1); tc::mbar_init(o_read + s, 4); tc::mbar_init(pv_done + s, 1);
     }
     tc::fence_barrier_init();
   }
@@ -162,16 +165,16 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
     // The whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues.
-    constexpr uint32_t idesc_qk = tc::make_idesc_tf32(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_qk = tc::make_idesc_tf32(BQ, BS, 0, 0);
     constexpr uint32_t idesc_pv = tc::make_idesc_tf32(BQ, DH, 0, 1);
     uint32_t kc = 0, vc = 0, ic = 0;
-    uint32_t pc[2] = {0, 0};          // P tiles consumed per group
     uint32_t oc[2] = {0, 0};          // items finished per group
-    // QK^T of key tile (stage ks) for group g into S_g
-    auto issue_qk = [&](int g, int ks) {
+    uint32_t tb[2] = {0, 0};          // key tiles of earlier items per group (phase base of s_full / p_full)
+    // S_g[buf] = Q_g K^T over the 64 keys `hh` of the key tile in stage ks
+    auto issue_qk = [&](int g, int ks, int hh) {
       const uint32_t sq = tc::smem_u32(smem + C::kOffQ + g * C::kTileBytes);
-      const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes);
-      const uint32_t d_tmem = tmem_base + C::kColS + g * BKV;
+      const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes) + hh * (BS * 128);
+      const uint32_t d_tmem = tmem_base + C::kColS + g * BKV + hh * BS;
       if (tc::elect_one()) {
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -181,7 +184,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           for (int k = 0; k < 4; ++k)
             tc::mma_tf32_ss(d_tmem, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
         }
-        tc::tc_commit(s_full + g);
+        tc::tc_commit(s_full + 2 * g + hh);
       }
       __syncwarp();
     };
@@ -190,12 +193,12 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       item_coords(item, b, h, q0, nA, nB);
       const int ng[2] = {nA, nB};
       tc::mbar_wait(q_full, ic & 1);
-      {   // key tile 0 for both query tiles
+      {   // key tile 0: both halves for both query tiles (S is double-buffered: the softmax never waits for its next S)
         const int ks = kc & 1;
         tc::mbar_wait(k_full + ks, (kc >> 1) & 1);
         tc::tc_fence_after();
-        issue_qk(0, ks);
-        issue_qk(1, ks);
+        issue_qk(0, ks, 0); issue_qk(1, ks, 0);
+        issue_qk(0, ks, 1); issue_qk(1, ks, 1);
         if (tc::elect_one()) { tc::tc_commit(k_empty + ks); if (nB == 1) tc::tc_commit(q_empty); }
         __syncwarp();
         ++kc;
@@ -210,25 +213,29 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // V tile: kChunks MN blocks (32 head-dim columns each) of 128 key rows x 128 B; 4-row swizzle atoms
         const uint64_t dv = tc::make_smem_desc(sv, BKV * 128, 512, tc::kLayoutSw128Base32);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (j >= ng[g]) continue;
-          tc::mbar_wait(p_full + g, pc[g] & 1);
-          ++pc[g];
-          if (j == 0) tc::mbar_wait(o_read + g, (oc[g] & 1) ^ 1);        // the previous item's O_g has been read out
-          tc::tc_fence_after();
-          const uint32_t a_tmem = tmem_base + C::kColS + g * BKV;
-          const uint32_t d_tmem = tmem_base + C::kColO + g * DH;
-          if (tc::elect_one()) {
+        for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-            for (int k = 0; k < BKV / 8; ++k)
-              tc::mma_tf32_ts(d_tmem, a_tmem + k * 8, tc::desc_advance(dv, k * 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-            if (j + 1 == ng[g]) tc::tc_commit(o_final + g);
-          }
-          __syncwarp();
-          if (j + 1 == ng[g]) ++oc[g];
-          if (j + 1 < ng[g]) {
-            if (!k_ready) { tc::mbar_wait(k_full + ks, (kc >> 1) & 1); tc::tc_fence_after(); k_ready = true; }
-            issue_qk(g, ks);
+          for (int g = 0; g < 2; ++g) {
+            if (j >= ng[g]) continue;
+            tc::mbar_wait(p_full + 2 * g + hh, (tb[g] + j) & 1);
+            if (j == 0 && hh == 0) tc::mbar_wait(o_read + g, (oc[g] & 1) ^ 1);        // the previous item's O_g has been read out
+            tc::tc_fence_after();
+            const uint32_t a_tmem = tmem_base + C::kColS + g * BKV + hh * BS;
+            const uint32_t d_tmem = tmem_base + C::kColO + g * DH;
+            const bool last = j + 1 == ng[g] && hh == 1;
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BS / 8; ++k)
+                tc::mma_tf32_ts(d_tmem, a_tmem + k * 8, tc::desc_advance(dv, (hh * (BS / 8) + k) * 1024), idesc_pv, (j > 0 || hh > 0 || k > 0) ? 1u : 0u);
+              tc::tc_commit(pv_done + g);
+              if (last) tc::tc_commit(o_final + g);
+            }
+            __syncwarp();
+            if (last) ++oc[g];
+            if (j + 1 < ng[g]) {       // the same half of the NEXT key tile into the S buffer this P V has just read
+              if (!k_ready) { tc::mbar_wait(k_full + ks, (kc >> 1) & 1); tc::tc_fence_after(); k_ready = true; }
+              issue_qk(g, ks, hh);
+            }
           }
         }
         if (tc::elect_one()) {
@@ -239,6 +246,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ++vc;
         if (more) ++kc;
       }
+      tb[0] += nA; tb[1] += nB;
     }
   }
   } else {
@@ -293,51 +301,49 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       };
       uint32_t w_pref[4] = {0u, 0u, 0u, 0u};
-      if (p.p_drop > 0.f) load_w(0, w_pref);
+      if (DROP) load_w(0, w_pref);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // the item's bias table is complete (both groups)
-      for (int j = 0; j < n; ++j) {
-        const int k0 = j * BKV;
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int t = 0; t < 2 * n; ++t) {                  // 64-key steps: half hh of key tile j
+        const int j = t >> 1, hh = t & 1;
+        const int k0 = j * BKV + hh * BS;
         TRACE(trole, 0);
-        uint32_t w[4];
+        if (hh == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = w_pref[i];
-        if (p.p_drop > 0.f && j + 1 < n) load_w(k0 + BKV, w_pref);
-        tc::mbar_wait(s_full + g, sc & 1);
-        ++sc;
+          for (int i = 0; i < 4; ++i) w[i] = w_pref[i];
+          if (DROP && j + 1 < n) load_w((j + 1) * BKV, w_pref);
+        }
+        tc::mbar_wait(s_full + 2 * g + hh, (sc / 2 + j) & 1);
         TRACE(trole, 2);
         tc::tc_fence_after();
-        float s[BKV];
+        const uint32_t s_tm = s_addr + hh * BS;
+        float s[BS];
         {
-          uint32_t r0[32], r1[32], r2[32], r3[32];         // all four 32-column chunks in flight before the single wait
-          tc::tmem_ld_32x32(s_addr, r0);
-          tc::tmem_ld_32x32(s_addr + 32, r1);
-          tc::tmem_ld_32x32(s_addr + 64, r2);
-          tc::tmem_ld_32x32(s_addr + 96, r3);
+          uint32_t r0[32], r1[32];                         // both 32-column chunks in flight before the single wait
+          tc::tmem_ld_32x32(s_tm, r0);
+          tc::tmem_ld_32x32(s_tm + 32, r1);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]);
-            s[64 + c] = __uint_as_float(r2[c]); s[96 + c] = __uint_as_float(r3[c]);
-          }
+          for (int c = 0; c < 32; ++c) { s[c] = __uint_as_float(r0[c]); s[32 + c] = __uint_as_float(r1[c]); }
         }
         TRACE(trole, 3);
-        const bool diag = p.causal && (k0 + BKV - 1 > q0g);
+        const bool diag = p.causal && (k0 + BS - 1 > q0g);
         const int fg = k0 >> 5;
-        const bool clean = !diag && (flag_it[fg] & flag_it[fg + 1] & flag_it[fg + 2] & flag_it[fg + 3]);
+        const bool clean = !diag && (flag_it[fg] & flag_it[fg + 1]);
         if (!clean) {
 #pragma unroll
-          for (int c = 0; c < BKV; c += 4) {
+          for (int c = 0; c < BS; c += 4) {
             const float4 bv = tc::ld_shared_v4(bias_u32 + 4 * (k0 + c));      // broadcast
             s[c] += bv.x; s[c + 1] += bv.y; s[c + 2] += bv.z; s[c + 3] += bv.w;
           }
           if (diag) {
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) s[c] = (k0 + c > qi) ? -INFINITY : s[c];
+            for (int c = 0; c < BS; ++c) s[c] = (k0 + c > qi) ? -INFINITY : s[c];
           }
         }
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < BKV; ++c) m4[c & 3] = fmaxf(m4[c & 3], s[c]);
+        for (int c = 0; c < BS; ++c) m4[c & 3] = fmaxf(m4[c & 3], s[c]);
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         TRACE(trole, 4);
         // lazy rescale: keep the stale maximum unless the new one exceeds it by more than 2^8 (or there is none yet)
@@ -345,8 +351,10 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (__any_sync(0xffffffffu, grow)) {
           const float corr = grow ? fast_exp2((m_used - mx) * p.scale_log2) : 1.f;      // m_used = -inf -> 0
           if (grow) { l_run *= corr; m_used = mx; }
-          if (j > 0) {
-            // PV_g(j-1) is complete (s_full of this tile was committed after it) and PV_g(j) waits for this tile's P
+          if (t > 0) {
+            // O_g holds PV_g(0..t-1): the last of them must have retired (PV_g(t) cannot start before this step's P)
+            tc::mbar_wait(pv_done + g, (sc + t - 1) & 1);
+            tc::tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < DH; c0 += 32) {
               uint32_t r[32];
@@ -360,29 +368,32 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         const float m_safe = m_used == -INFINITY ? 0.f : m_used;
         const float neg_ms = -m_safe * p.scale_log2;
+        // exp2, row sum, dropout, TF32 rounding and the TMEM store of P chunk by chunk in ONE basic block (DROP is a template
+        // constant): the scheduler overlaps the MUFU queue of one 32-column chunk with the ALU work of its neighbours
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < BKV; ++c) { s[c] = fast_exp2(fmaf(s[c], p.scale_log2, neg_ms)); rs4[c & 3] += s[c]; }
+        for (int c0 = 0; c0 < BS; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t wd = w[2 * hh + (c0 >> 5)];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float e = fast_exp2(fmaf(s[c0 + c], p.scale_log2, neg_ms));
+            rs4[c & 3] += e;
+            if (DROP) e = ((wd >> c) & 1u) ? e : 0.f;               // x 1/(1-p) folded into the final scale
+            r[c] = tf32_rn_finite_bits(e);                          // P >= 0, finite
+          }
+          tc::tmem_st_32x32(s_tm + c0, r);
+        }
         l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         TRACE(trole, 5);
-        if (p.p_drop > 0.f) {
-#pragma unroll
-          for (int c = 0; c < BKV; ++c) s[c] = ((w[c >> 5] >> (c & 31)) & 1u) ? s[c] : 0.f;   // x 1/(1-p) folded into the final scale
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          uint32_t r[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = tf32_rn_finite_bits(s[c0 + c]);      // P >= 0, finite
-          tc::tmem_st_32x32(s_addr + c0, r);
-        }
         tc::tmem_st_wait();
         TRACE(trole, 6);
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(p_full + g);
+        if (lane == 0) tc::mbar_arrive(p_full + 2 * g + hh);
         TRACE(trole, 7);
       }
+      sc += 2 * n;                                       // P V steps of this group so far (pv_done phases)
       // the next item's table is built here: its key-padding loads overlap the wait for this item's last P V
       if (item + (int)gridDim.x < p.items) build_table(item + gridDim.x, itc + 1);
       tc::mbar_wait(o_final + g, fc & 1);
@@ -453,11 +464,18 @@ int launch(const pa_attn_fwd_args& a, cudaStream_t st) {
   p.kv_len = a.kpm != nullptr ? a.kv_len : nullptr;
   const int smem_bytes = C::kSmemFixed + 2 * p.LkPad * 4;
   if (smem_bytes > 227 * 1024 || p.LkPad > 2048) { pa_set_error("pa_attn_fwd (tc): Lk = %d too long for the bias table", a.Lk); return PA_ERR_UNSUPPORTED; }
-  auto kern = attn_fwd_pp_kernel<DH>;
-  static SmemAttrCache attr;
-  if (int rc_attr = pa_set_max_smem(kern, smem_bytes, attr)) return rc_attr;
   int grid = p.items < pa_num_sms() ? p.items : pa_num_sms();
-  kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
+  if (a.p_drop > 0.f) {
+    auto kern = attn_fwd_pp_kernel<DH, true>;
+    static SmemAttrCache attr;
+    if (int rc_attr = pa_set_max_smem(kern, smem_bytes, attr)) return rc_attr;
+    kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
+  } else {
+    auto kern = attn_fwd_pp_kernel<DH, false>;
+    static SmemAttrCache attr;
+    if (int rc_attr = pa_set_max_smem(kern, smem_bytes, attr)) return rc_attr;
+    kern<<<grid, kThreads, smem_bytes, st>>>(tq, tk, tv, p);
+  }
   PA_CHECK_LAUNCH();
   return PA_OK;
 }
