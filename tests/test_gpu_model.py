@@ -256,10 +256,14 @@ def test_dropout_follows_torch_rng_state():
     l2, g2 = step_loss()
     torch.manual_seed(5)
     l1b, g1b = step_loss()
-    assert l1 == l1b and torch.equal(g1, g1b) and l1 != l2
+    # same masks => same step up to the summation order of the fp32 atomics (loss / split-K reductions: a few ulp);
+    # different masks move the loss by orders of magnitude more
+    def same(la, ga, lb, gb):
+        return abs(la - lb) <= 2e-6 * abs(la) and (ga - gb).abs().max().item() <= 1e-5 * ga.abs().max().item()
+    assert same(l1, g1, l1b, g1b) and abs(l1 - l2) > 1e-4 * abs(l1)
     torch.cuda.set_rng_state(state)
     l2b, g2b = step_loss()
-    assert l2 == l2b and torch.equal(g2, g2b)
+    assert same(l2, g2, l2b, g2b)
     torch.manual_seed(6)
     assert step_loss()[0] != l1
 
