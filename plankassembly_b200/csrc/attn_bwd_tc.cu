@@ -435,6 +435,7 @@ template <int DH> struct CfgK {
   static constexpr int kOffStat = kOffBar + 256;                      // [2 items][lse2 | delta][LqPad], sized at launch
   static constexpr int kSmemFixed = kOffStat + 1024;                  // + 2 * 2 * LqPad * 4
   static constexpr int kColS = 0, kColDP = 128, kColDK = 256, kColDV = 256 + DH;
+  static constexpr int kColK = 384, kColV = 448;         // the stationary K_j / V_j tiles as TMEM A-operands of S^T / dP^T
   static constexpr int kTmemCols = 512;
 };
 
@@ -458,13 +459,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   uint64_t* qm_full = bars + 12;  uint64_t* qm_empty = bars + 14;    // [2] each: MN-major halves
   uint64_t* st_full = bars + 6;   uint64_t* pds_full = bars + 8;     // [2] each
   uint64_t* acc_full = bars + 10; uint64_t* acc_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kt_full = bars + 16;                                     // K_j / V_j copied into TMEM by the elementwise warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v); tc::tma_prefetch_desc(&tm_q);
     tc::tma_prefetch_desc(&tm_q_mn); tc::tma_prefetch_desc(&tm_do); tc::tma_prefetch_desc(&tm_do_mn);
-    tc::mbar_init(kv_full, 1); tc::mbar_init(kv_empty, 1);
+    tc::mbar_init(kv_full, 1); tc::mbar_init(kv_empty, 8); tc::mbar_init(kt_full, 8);
     for (int s = 0; s < C::kStages; ++s) {
       tc::mbar_init(q_full + s, 1); tc::mbar_init(q_empty + s, 1);
       tc::mbar_init(qm_full + s, 1); tc::mbar_init(qm_empty + s, 1);
@@ -531,7 +533,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       constexpr uint32_t idesc_acc = tc::make_idesc_tf32(C::BKV, DH, 0, 1);       // [128 keys x DH]
       TRACE_DECL(lane == 0);
       uint32_t qc = 0, ic = 0, st = 0, dt = 0;
-      const uint32_t sk = tc::smem_u32(smem + C::kOffK), sv = tc::smem_u32(smem + C::kOffV);
+      // S^T / dP^T take K_j / V_j from TMEM (tcgen05.mma with a TMEM A-operand: 32 cycles per 128x64x8 step; the SS form also
+      // reads 4 KB of A from shared memory per step and needs 48 -- scripts/probe/mma_rate.cu -- and this kernel is bound by
+      // its 32 MMAs per 64-query step)
       auto issue_st = [&](uint32_t qcs) {
         const int s = qcs % C::kStages;
         tc::mbar_wait(q_full + s, (qcs / C::kStages) & 1);
@@ -543,19 +547,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         if (tc::elect_one()) {
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
-            const uint64_t da = tc::make_smem_desc(sk + c * (C::BKV * 128), 16, 1024);
             const uint64_t db = tc::make_smem_desc(sq + c * (C::BQ * 128), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc::mma_tf32_ss(tmem_base + C::kColS + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+              tc::mma_tf32_ts(tmem_base + C::kColS + buf * C::BQ, tmem_base + C::kColK + c * 32 + k * 8, tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
           }
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
-            const uint64_t da = tc::make_smem_desc(sv + c * (C::BKV * 128), 16, 1024);
             const uint64_t db = tc::make_smem_desc(sdo + c * (C::BQ * 128), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc::mma_tf32_ss(tmem_base + C::kColDP + buf * C::BQ, tc::desc_advance(da, k * 32), tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+              tc::mma_tf32_ts(tmem_base + C::kColDP + buf * C::BQ, tmem_base + C::kColV + c * 32 + k * 8, tc::desc_advance(db, k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
           }
           tc::tc_commit(q_empty + s);                    // the K-major halves are free once these retire
           tc::tc_commit(st_full + buf);
@@ -568,13 +570,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         int b, h, k0, i0;
         coords(item, b, h, k0, i0);
         const int n = q_tiles_all - i0;
-        tc::mbar_wait(kv_full, ic & 1);
+        tc::mbar_wait(kt_full, ic & 1);                  // K_j / V_j are in TMEM (the elementwise warps released the smem tiles)
         tc::tc_fence_after();
         if (n > 0) issue_st(qc);
         else tc::mbar_wait(acc_empty, (ic & 1) ^ 1);
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_st(qc + 1);
-          if (j + 1 == n) { if (tc::elect_one()) tc::tc_commit(kv_empty); __syncwarp(); }       // K_j / V_j no longer needed once these retire
           const int buf = dt & 1;
           if (j == 0) tc::mbar_wait(acc_empty, (ic & 1) ^ 1);    // previous item's dK/dV have been read out of TMEM
           tc::mbar_wait(pds_full + buf, (dt >> 1) & 1);
@@ -602,10 +603,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           TRACE(1, 4);
           ++qc; ++dt;
         }
-        if (tc::elect_one()) {
-          if (n == 0) tc::tc_commit(kv_empty);
-          tc::tc_commit(acc_full);
-        }
+        if (tc::elect_one()) tc::tc_commit(acc_full);
         __syncwarp();
       }
       TRACE_END(1);
@@ -647,8 +645,33 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
       }
       r.mw0 = p.p_drop > 0.f ? load_mw_at(r.b, r.h, r.kj, r.i0 * C::BQ) : 0xffffffffu;
     };
+    // stationary operands: this thread's row of K_j and V_j (its warpgroup's 32-column chunk) from the TMA tiles in shared
+    // memory (128B swizzle: 16-byte piece i of row r sits at piece i ^ (r & 7)) into TMEM.  Called when these warps have
+    // consumed every S^T / dP^T of the previous item, so the TMEM columns are free; the smem tiles are released at once.
+    auto copy_kv = [&](uint32_t icn) {
+      tc::mbar_wait(kv_full, icn & 1);
+      if (half < C::kChunks) {
+        const uint32_t krow = tc::smem_u32(smem + C::kOffK + half * (C::BKV * 128) + row * 128);
+        const uint32_t vrow = tc::smem_u32(smem + C::kOffV + half * (C::BKV * 128) + row * 128);
+        uint32_t rk[32], rv[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int off = (i ^ (row & 7)) << 4;
+          const float4 a4 = tc::ld_shared_v4(krow + off);
+          const float4 d4 = tc::ld_shared_v4(vrow + off);
+          rk[4 * i] = __float_as_uint(a4.x); rk[4 * i + 1] = __float_as_uint(a4.y); rk[4 * i + 2] = __float_as_uint(a4.z); rk[4 * i + 3] = __float_as_uint(a4.w);
+          rv[4 * i] = __float_as_uint(d4.x); rv[4 * i + 1] = __float_as_uint(d4.y); rv[4 * i + 2] = __float_as_uint(d4.z); rv[4 * i + 3] = __float_as_uint(d4.w);
+        }
+        tc::tmem_st_32x32(tmem_base + lane_addr + C::kColK + half * 32, rk);
+        tc::tmem_st_32x32(tmem_base + lane_addr + C::kColV + half * 32, rv);
+        tc::tmem_st_wait();
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(kt_full); tc::mbar_arrive(kv_empty); }
+    };
     ItemRegs nx;
-    if ((int)blockIdx.x < p.items) prefetch(blockIdx.x, nx);
+    if ((int)blockIdx.x < p.items) { prefetch(blockIdx.x, nx); copy_kv(0); }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
       const ItemRegs cu = nx;
       const int b = cu.b, h = cu.h, k0 = cu.k0, i0 = cu.i0, kj = cu.kj;
@@ -733,7 +756,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         if (lane == 0) tc::mbar_arrive(pds_full + buf);
         TRACE(trole, 6);
       }
-      if (item + (int)gridDim.x < p.items) prefetch(item + gridDim.x, nx);    // next item's loads fly during the read-out
+      if (item + (int)gridDim.x < p.items) {
+        prefetch(item + gridDim.x, nx);                  // next item's loads fly during the read-out
+        copy_kv(ic + 1);                                 // and its K / V go into TMEM: the tensor pipe starts on it meanwhile
+      }
       tc::mbar_wait(acc_full, ic & 1);
       TRACE(trole, 7);
       tc::tc_fence_after();
