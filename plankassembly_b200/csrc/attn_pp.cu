@@ -15,7 +15,7 @@
 //     O handshake disappears;
 //   * S and P share one TMEM buffer per tile (P overwrites S; the in-order tensor pipe makes PV_g(j) read it before
 //     QK_g(j+1) overwrites it).
-// TMEM: S_A | S_B (2 x 128 columns), O_A | O_B (2 x DH).  Shared memory: Q_A, Q_B, two K stages, two V stages (32 KB each
+// TMEM: S_A | S_B (2 x 128 columns), O_A | O_B (2 x DH), Q_A | Q_B (2 x DH: A-operands of QK^T).  Shared memory: Q_A, Q_B, two K stages, two V stages (32 KB each
 // at DH = 64) + the per-item key-bias tables.
 // Used when the number of query tiles is even; attn_tc.cu keeps odd counts (a single 128-row tile: T = 128).
 //   Reference: torch nn/functional.py multi_head_attention_forward as reached from ref models.py:206,212.
@@ -60,6 +60,7 @@ template <int DH> struct Cfg {
   static constexpr int kTmemCols = 512;
   static constexpr int kColS = 0;                          // + g * 128
   static constexpr int kColO = 256;                        // + g * DH
+  static constexpr int kColQ = 384;                        // + g * DH: the stationary Q tiles as TMEM A-operands of QK^T
 };
 
 struct Params {
@@ -95,18 +96,19 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* o_final = bars + 18;          // [2 groups]  last PV_g of the item complete
   uint64_t* o_read = bars + 20;           // [2 groups]  O_g read out: the next item's PV_g(0) may overwrite it
   uint64_t* pv_done = bars + 22;          // [2 groups]  PV_g(t) complete (waited for only before a rescale of O_g)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* qt_full = bars + 24;          // [2 groups]  Q_g copied into TMEM by its softmax warpgroup
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
-    tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
+    tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 8);
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1);
       tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 1);
       tc::mbar_init(s_full + 2 * s, 1); tc::mbar_init(s_full + 2 * s + 1, 1);
       tc::mbar_init(p_full + 2 * s, 4); tc::mbar_init(p_full + 2 * s + 1, 4);
-      tc::mbar_init(o_final + s, 1); tc::mbar_init(o_read + s, 4); tc::mbar_init(pv_done + s, 1);
+      tc::mbar_init(o_final + s, 1); tc::mbar_init(o_read + s, 4); tc::mbar_init(pv_done + s, 1); tc::mbar_init(qt_full + s, 4);
     }
     tc::fence_barrier_init();
   }
@@ -172,17 +174,16 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     uint32_t tb[2] = {0, 0};          // key tiles of earlier items per group (phase base of s_full / p_full)
     // S_g[buf] = Q_g K^T over the 64 keys `hh` of the key tile in stage ks
     auto issue_qk = [&](int g, int ks, int hh) {
-      const uint32_t sq = tc::smem_u32(smem + C::kOffQ + g * C::kTileBytes);
       const uint32_t sk = tc::smem_u32(smem + C::kOffK + ks * C::kTileBytes) + hh * (BS * 128);
       const uint32_t d_tmem = tmem_base + C::kColS + g * BKV + hh * BS;
+      const uint32_t a_tmem = tmem_base + C::kColQ + g * DH;
       if (tc::elect_one()) {
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
-          const uint64_t dq = tc::make_smem_desc(sq + c * (BQ * 128), 16, 1024);
           const uint64_t dk = tc::make_smem_desc(sk + c * (BKV * 128), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::mma_tf32_ss(d_tmem, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)      // A = Q_g from TMEM: 32 cycles per 128x64x8 step instead of 48 with A in shared memory
+            tc::mma_tf32_ts(d_tmem, a_tmem + c * 32 + k * 8, tc::desc_advance(dk, k * 32), idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
         }
         tc::tc_commit(s_full + 2 * g + hh);
       }
@@ -192,14 +193,15 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       int b, h, q0, nA, nB;
       item_coords(item, b, h, q0, nA, nB);
       const int ng[2] = {nA, nB};
-      tc::mbar_wait(q_full, ic & 1);
+      tc::mbar_wait(qt_full + 0, ic & 1);               // Q_A / Q_B are in TMEM (their smem tiles are already released)
+      tc::mbar_wait(qt_full + 1, ic & 1);
       {   // key tile 0: both halves for both query tiles (S is double-buffered: the softmax never waits for its next S)
         const int ks = kc & 1;
         tc::mbar_wait(k_full + ks, (kc >> 1) & 1);
         tc::tc_fence_after();
         issue_qk(0, ks, 0); issue_qk(1, ks, 0);
         issue_qk(0, ks, 1); issue_qk(1, ks, 1);
-        if (tc::elect_one()) { tc::tc_commit(k_empty + ks); if (nB == 1) tc::tc_commit(q_empty); }
+        if (tc::elect_one()) tc::tc_commit(k_empty + ks);
         __syncwarp();
         ++kc;
       }
@@ -240,7 +242,7 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         if (tc::elect_one()) {
           tc::tc_commit(v_empty + vs);
-          if (more) { tc::tc_commit(k_empty + ks); if (j + 2 == nB) tc::tc_commit(q_empty); }     // that was the last QK^T of this item
+          if (more) tc::tc_commit(k_empty + ks);
         }
         __syncwarp();
         ++vc;
@@ -302,6 +304,27 @@ attn_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       };
       uint32_t w_pref[4] = {0u, 0u, 0u, 0u};
       if (DROP) load_w(0, w_pref);
+      {
+        // stationary operand: this thread's row of Q_g from the TMA tile in shared memory (128B swizzle: 16-byte piece i of
+        // row r sits at piece i ^ (r & 7)) into TMEM.  Every QK^T of the previous item has retired (this group consumed all
+        // of its S tiles), so the TMEM columns are free; the smem tile is released as soon as both groups have copied.
+        tc::mbar_wait(q_full, itc & 1);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          const uint32_t qrow = tc::smem_u32(smem + C::kOffQ + g * C::kTileBytes + c * (BQ * 128) + row * 128);
+          uint32_t rq[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a4 = tc::ld_shared_v4(qrow + ((i ^ (row & 7)) << 4));
+            rq[4 * i] = __float_as_uint(a4.x); rq[4 * i + 1] = __float_as_uint(a4.y); rq[4 * i + 2] = __float_as_uint(a4.z); rq[4 * i + 3] = __float_as_uint(a4.w);
+          }
+          tc::tmem_st_32x32(tmem_base + lane_addr + C::kColQ + g * DH + c * 32, rq);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { tc::mbar_arrive(qt_full + g); tc::mbar_arrive(q_empty); }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");      // the item's bias table is complete (both groups)
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       for (int t = 0; t < 2 * n; ++t) {                  // 64-key steps: half hh of key tile j

@@ -9,6 +9,9 @@
 #include <stdlib.h>
 
 constexpr int kLnWarps = 4;
+#ifndef PA_LN_BWD_MIN_BLOCKS
+#define PA_LN_BWD_MIN_BLOCKS 4
+#endif
 // The row-per-warp kernels issue a row's loads, reduce, store, and only then touch the next row: with few resident warps
 // (the backward needs 148 registers: 12 warps per SM) too few bytes are in flight to cover the DRAM latency (ncu: 3.0 TB/s).
 // Each warp therefore pulls the rows it will process NEXT into L2 while it works on the current one (no registers, no smem).
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const float4*
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
+__global__ void __launch_bounds__(kLnWarps * 32, NV <= 4 ? PA_LN_BWD_MIN_BLOCKS : 2) add_ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ s,
                                                                      const float2* __restrict__ stats, const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                                                      float p_drop, uint64_t seed, uint64_t offset, int64_t rows,
                                                                      float4* __restrict__ dx, float4* __restrict__ da, int round_da, int want_dabias, float* __restrict__ partial,
