@@ -310,15 +310,22 @@ def run_train(args, rank, world, local_rank):
     }
     # TF32 kind::tf32 MMAs run at half the bf16 rate: `peak` stays the measured bf16 number the contract names, `peak_tf32`
     # (= peak / 2) is the ceiling a TF32 kernel can actually reach.
+    # `traffic`: dram__bytes_read + dram__bytes_write per launch of the family, OFFLINE from the ncu pass over one step of this
+    # workload (profiles/r2b_step_metrics_summary.txt: GEMMs 23.04 GB over 205 launches; attention fwd + dQ + dK/dV + delta
+    # 13.82 GB over 72 kernels = 36 calls) -- not measured by this run; only quoted for the workload it was captured on
+    offline = args.workload == 'config2' and B == 64
     for key, names, label, traffic in (
-            ('roofline', ['pa_gemm_tf32'], 'pa_gemm_tf32 (all projections, FFN, heads, pointer scores: fwd + dX + dW)', None),
-            ('roofline_attention', ['pa_attn_fwd', 'pa_attn_bwd'], 'pa_attn_fwd + pa_attn_bwd (delta + dQ + dK/dV)', None)):
+            ('roofline', ['pa_gemm_tf32'], 'pa_gemm_tf32 (all projections, FFN, heads, pointer scores: fwd + dX + dW)',
+             23.04e9 / 205 if offline else None),
+            ('roofline_attention', ['pa_attn_fwd', 'pa_attn_bwd'], 'pa_attn_fwd + pa_attn_bwd (delta + dQ + dK/dV)',
+             13.82e9 / 36 if offline else None)):
         n_l, t_ms, fl = family(names)
         if n_l:
             ach = fl / (t_ms / 1e3) / 1e12
             res[key] = {'bound': 'tensor', 'kernel': label, 'achieved': ach, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                         'frac': ach / pk['tf_sustained'], 'peak_tf32': pk['tf_sustained'] / 2, 'frac_tf32': ach / (pk['tf_sustained'] / 2),
-                        'traffic': traffic, 'peak_source': pk['src'] + ': sustained bf16 cuBLAS; a kind::tf32 kernel tops out at half of it',
+                        'traffic': traffic, 'traffic_source': 'offline: ncu pass over one step, profiles/r2b_step_metrics_summary.txt (bytes per launch)' if traffic else None,
+                        'peak_source': pk['src'] + ': sustained bf16 cuBLAS; a kind::tf32 kernel tops out at half of it',
                         'avg_launch_ms': t_ms / n_l, 'launches_per_step': n_l / prof_steps, 'ms_per_step': t_ms / prof_steps,
                         'flop_per_launch': fl / n_l, 'share_of_step': (t_ms / prof_steps) / ms_step,
                         'how': f'CUDA events around every call for {prof_steps} extra steps after the headline timing'}
