@@ -59,6 +59,7 @@ struct BwdParams {
   int LkPad;             // keys rounded up to the key tile (per-item bias table length)
   int LqPad;             // queries rounded up to the query tile (per-item lse/delta table length)
   int trace;
+  int l2_prefetch;       // producers pull the tiles of a stage's NEXT use into L2 (PLANK_B200_ATTN_L2PF=1; measured: no gain, 347.4 vs 348.5 us, off)
 };
 
 // ================================================================================================
@@ -141,6 +142,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         for (int j = 0; j < n; ++j, ++kc) {
           const int s = kc % C::kStages;
+          if (p.l2_prefetch && j + C::kStages < n) {      // the tiles this stage will receive NEXT time, into L2 now
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+              tc::tma_prefetch_l2_2d(&tm_k, h * DH + c * 32, b * p.Lk + (j + C::kStages) * C::BK);
+              tc::tma_prefetch_l2_2d(&tm_v, h * DH + c * 32, b * p.Lk + (j + C::kStages) * C::BK);
+            }
+          }
           tc::mbar_wait(kv_empty + s, ((kc / C::kStages) & 1) ^ 1);
           TRACE(0, 1);
           tc::mbar_arrive_expect_tx(kv_full + s, C::kStageBytes);
@@ -491,6 +499,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   };
 
   if (warp == 0) {
+    // Two independent producers (lanes 0 and 1): the K-major copies of Q_i / dO_i (operands of S^T / dP^T) are released one
+    // MMA block earlier than the MN-major copies (operands of dV / dK).  One thread walking both in turn waited for the late
+    // release before it could issue the next early load, and the MMA issuer then waited ~500 cycles per step for that load
+    // (timeline: profiles/r2b_attn_bwd_dkdv_trace.txt).
     if (lane == 0) {
       uint32_t qc = 0, ic = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
@@ -507,6 +519,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
           const int s = qc % C::kStages;
           uint8_t* base = smem + C::kOffQ + s * C::kStageBytes;
           const int y = b * p.Lq + i * C::BQ;
+          if (p.l2_prefetch && i + C::kStages < q_tiles_all) {      // the tiles this stage will receive NEXT time, into L2 now
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+              tc::tma_prefetch_l2_2d(&tm_q, h * DH + c * 32, y + C::kStages * C::BQ);
+              tc::tma_prefetch_l2_2d(&tm_do, h * DH + c * 32, y + C::kStages * C::BQ);
+            }
+          }
           tc::mbar_wait(q_empty + s, ((qc / C::kStages) & 1) ^ 1);
           tc::mbar_arrive_expect_tx(q_full + s, 2 * C::kQBytes);
 #pragma unroll
@@ -515,6 +534,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             tc::tma_load_2d(base + off, &tm_q, x, y, q_full + s);
             tc::tma_load_2d(base + 2 * C::kQBytes + off, &tm_do, x, y, q_full + s);
           }
+        }
+      }
+    } else if (lane == 1) {
+      uint32_t qc = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int b, h, k0, i0;
+        coords(item, b, h, k0, i0);
+        for (int i = i0; i < q_tiles_all; ++i, ++qc) {
+          const int s = qc % C::kStages;
+          uint8_t* base = smem + C::kOffQ + s * C::kStageBytes;
+          const int y = b * p.Lq + i * C::BQ;
           tc::mbar_wait(qm_empty + s, ((qc / C::kStages) & 1) ^ 1);
           tc::mbar_arrive_expect_tx(qm_full + s, 2 * C::kQBytes);
 #pragma unroll
@@ -835,6 +865,7 @@ int launch(const pa_attn_bwd_args& a, cudaStream_t st) {
   p.wide_st = ((((uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 31) == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0) ? 1 : 0;
 #ifdef PA_ATTN_TRACE
   { const char* dbg = getenv("PLANK_B200_ATTN_DEBUG"); p.trace = dbg ? (atoi(dbg) & (1024 | 2048)) : 0; }
+  { const char* e = getenv("PLANK_B200_ATTN_L2PF"); p.l2_prefetch = e ? atoi(e) : 0; }
 #endif
   if (a.p_drop > 0.f && (a.drop_rows == nullptr || a.drop_cols == nullptr)) {
     pa_set_error("pa_attn_bwd (tc): p_drop > 0 needs drop_rows/drop_cols from pa_dropout_mask");

@@ -63,6 +63,11 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensor
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
       : "memory");
 }
+// pull a tile into L2 ahead of the load that will stage it (no shared memory, no barrier): hides the DRAM part of the TMA
+// round trip when there are too few stages to cover it
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
