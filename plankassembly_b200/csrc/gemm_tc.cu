@@ -486,7 +486,7 @@ int launch_cl(const pa_gemm_args& a, cudaStream_t st) {
   p.wide8 = (a.ldc % 8 == 0) && (((uintptr_t)a.c & 31) == 0) && (a.c_batch_stride % 8 == 0);
   if (p.epi_direct == 2 && !p.accumulate) p.tma_store = 0;
   p.mask_out = a.mask_out; p.mask_in = a.mask_in; p.colsum = a.colsum; p.mask_scale = a.mask_scale;
-  if (p.mask_out != nullptr || p.mask_in != nullptr || p.colsum != nullptr) p.tma_store = 0;      // lives in the register-direct epilogue
+  // (the bit-plane mask / column-sum stages run before the store stage: the fused FFN GEMMs take the TMA-store path too)
   if (p.tma_store) {
     rc = pa_make_tmap_2d(&tc_map, a.c, (uint64_t)a.N, (uint64_t)p.batch * a.M, (uint64_t)a.ldc * 4, 32, 32);
     if (rc) return rc;
