@@ -182,6 +182,7 @@ class PlankModel(nn.Module):
 
     def _decode_train(self, y, y_r, memory_r, in_kpm, out_kpm):
         p, H, d, tf = self._p(), self.num_head, self.num_model, self._tf32()
+        mem_acc = ops.DxAccum() if (tf and ops.DX_ACCUM) else None      # the memory's gradient: summed inside the dX GEMM epilogues
         for layer in self.decoder.layers:
             sa, ca = layer.self_attn, layer.multihead_attn
             qkv = ops.linear(y_r, sa.in_proj_weight, sa.in_proj_bias, tf32=tf, round_out=True, bias_grad=False)
@@ -189,7 +190,8 @@ class PlankModel(nn.Module):
             a = ops.linear(a, sa.out_proj.weight, None if tf else sa.out_proj.bias, tf32=tf, round_dx=True)
             y, y_r = self._add_ln(y, a, layer.norm1, self.layer_eps, p, tf, sa.out_proj.bias)
             q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True, bias_grad=False)
-            kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True, bias_grad=False)
+            kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True, bias_grad=False,
+                            dx_accum=mem_acc)
             a = ops.CrossAttention.apply(q, kv, ca.in_proj_bias if tf else None, in_kpm, H, p, self._impl(), tf)
             a = ops.linear(a, ca.out_proj.weight, None if tf else ca.out_proj.bias, tf32=tf, round_dx=True)
             y, y_r = self._add_ln(y, a, layer.norm2, self.layer_eps, p, tf, ca.out_proj.bias)

@@ -535,6 +535,17 @@ def linear_x3(x, W, b, rows=None, relu=False, out=None):
     return y.view(*x.shape[:-1], N)
 
 
+class DxAccum:
+    """One input-gradient buffer shared by SEVERAL Linear nodes that read the same activation (the encoder memory feeds the
+    cross-attention K/V projection of every decoder layer): the first backward to run stores its dx, the others add theirs
+    into it in the GEMM epilogue (TMA reduce-add) and hand autograd no gradient of their own, so the sum costs no extra
+    kernels (it was five elementwise adds of the [B,S,d] gradient per step).  Stream order makes the buffer complete before
+    the producer's backward reads it: autograd runs that node only after all the sharing nodes have been enqueued."""
+
+    def __init__(self):
+        self.buf, self.n_fwd, self.n_bwd = None, 0, 0
+
+
 class Linear(Function):
     """y = x W^T + b (optionally relu + dropout fused in the GEMM epilogue) on the TF32 tensor cores.
     x must already be TF32-rounded by its producer; W_r is the rounded shadow of W (W itself only routes
@@ -543,8 +554,12 @@ class Linear(Function):
     round_out / round_dx: y / dx feed tensor-core operands only and are written rounded."""
 
     @staticmethod
-    def forward(ctx, x, W, b, W_r, relu, p_drop, round_out, round_dx):
+    def forward(ctx, x, W, b, W_r, relu, p_drop, round_out, round_dx, *extra):       # extra: an optional DxAccum
         _require_cuda(x, W)
+        dx_accum = extra[0] if extra else None
+        ctx.dx_accum, ctx.n_extra = dx_accum, len(extra)
+        if dx_accum is not None:
+            dx_accum.n_fwd += 1
         K, N = W.shape[1], W.shape[0]
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
@@ -585,7 +600,17 @@ class Linear(Function):
             ldn = (N + 3) // 4 * 4
             dy2 = torch.nn.functional.pad(dy2, (0, ldn - N))
         dx = dW = None
-        if ctx.needs_input_grad[0]:
+        acc = ctx.dx_accum
+        if ctx.needs_input_grad[0] and acc is not None and not round_dx and K % 4 == 0:
+            first = acc.buf is None
+            if first:
+                acc.buf = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+            gemm_tf32(dy2, W_r, acc.buf, M, K, N, lda=ldn, ldb=W_r.stride(0), ldc=K, b_mn=True, accumulate=not first)
+            dx = acc.buf.view(xshape) if first else None        # the later nodes add in place: no gradient of their own
+            acc.n_bwd += 1
+            if acc.n_bwd == acc.n_fwd:                           # a second backward over the same graph starts afresh
+                acc.buf, acc.n_bwd = None, 0
+        elif ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
             gemm_tf32(dy2, W_r, dx, M, K, N, lda=ldn, ldb=W_r.stride(0), ldc=K, b_mn=True, round_out=round_dx)
             dx = dx.view(xshape)
@@ -594,7 +619,7 @@ class Linear(Function):
             tiles = ((N + 127) // 128) * ((K + 255) // 256 if K % 256 == 0 else (K + 127) // 128)
             gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
-        return dx, dW, db, None, None, None, None, None
+        return (dx, dW, db, None, None, None, None, None) + (None,) * ctx.n_extra
 
 
 class FFN(Function):
@@ -690,9 +715,10 @@ def pointer_scores(pf, h, tf32):
 
 GEMM_IMPL = os.environ.get('PLANK_B200_GEMM', 'tc')
 FFN_FUSED = os.environ.get('PLANK_B200_FFN_FUSED', '1') == '1'        # A/B switch for ops.FFN
+DX_ACCUM = os.environ.get('PLANK_B200_DX_ACCUM', '1') == '1'          # A/B switch for ops.DxAccum (shared input gradients)
 
 
-def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True):
+def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True, dx_accum=None):
     """Dense projection y = x W[rows]^T + b[rows].
     tf32=True : our tcgen05 TF32 GEMM (training path; x must be a TF32-rounded tensor).
     tf32=False: fp32-class result.  Without autograd (inference) it is the same tcgen05 kernel fed error-compensated
@@ -704,7 +730,7 @@ def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=Fal
         bv = bv.detach()                 # bias is added here, its gradient comes from the consumer kernel
     if tf32:
         W_r = tf32_weight(W)
-        return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx)
+        return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx, dx_accum)
     if GEMM_IMPL == 'tc' and not torch.is_grad_enabled() and p_drop == 0.0 and W.shape[1] % 4 == 0:
         return linear_x3(x, W, b, rows, relu)        # inference: our own tensor-core kernel in 3xTF32, no cuBLAS
     y = torch.nn.functional.linear(x, Wv, bv)

@@ -252,3 +252,32 @@ def test_fused_ffn_matches_the_two_linears(M, d, ff, p):
 
 def ops_round(t):
     return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def test_shared_input_gradient_accumulates_in_the_epilogue():
+    """ops.DxAccum: several Linear nodes reading the SAME activation sum their input gradients inside the dX GEMM epilogues
+    (first node stores, the others TMA reduce-add) -- same result as autograd's own accumulation, also on a second backward."""
+    from plankassembly_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 1196, 512, 1024
+    x0 = ops_round(torch.randn(M, K, generator=g)).cuda()
+    Ws = [(torch.randn(N, K, generator=g) / K ** 0.5).cuda() for _ in range(3)]
+    ws = [torch.randn(M, N, generator=g).cuda() for _ in range(3)]
+    res = []
+    for shared in (True, False):
+        x = x0.clone().requires_grad_(True)
+        params = [w.clone().requires_grad_(True) for w in Ws]
+        ops.begin_step()
+        acc = ops.DxAccum() if shared else None
+        outs = [ops.linear(x, p, None, tf32=True, dx_accum=acc) for p in params]
+        loss = sum((o * w).sum() for o, w in zip(outs, ws))
+        loss.backward(retain_graph=shared)
+        g1, gp = x.grad.clone(), [p.grad.clone() for p in params]
+        if shared:                      # a second pass over the same graph must start from a fresh buffer
+            x.grad = None
+            loss.backward()
+            assert rel_err(x.grad.cpu(), g1.cpu()) < 1e-6
+        res.append((g1, gp))
+    assert rel_err(res[0][0].cpu(), res[1][0].cpu()) < 2e-6          # fp32 sums in another order
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_err(a.cpu(), b.cpu()) < 1e-5     # split-K reduce-add order
