@@ -189,9 +189,10 @@ class PlankModel(nn.Module):
             a = ops.SelfAttention.apply(qkv, sa.in_proj_bias if tf else None, out_kpm, H, True, p, self._impl(), tf)
             a = ops.linear(a, sa.out_proj.weight, None if tf else sa.out_proj.bias, tf32=tf, round_dx=True)
             y, y_r = self._add_ln(y, a, layer.norm1, self.layer_eps, p, tf, sa.out_proj.bias)
-            q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True, bias_grad=False)
+            w_acc = ops.DxAccum() if tf else None           # one in-projection weight gradient for the q rows and the k/v rows
+            q = ops.linear(y_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(0, d), tf32=tf, round_out=True, bias_grad=False, w_accum=w_acc)
             kv = ops.linear(memory_r, ca.in_proj_weight, ca.in_proj_bias, rows=slice(d, 3 * d), tf32=tf, round_out=True, bias_grad=False,
-                            dx_accum=mem_acc)
+                            dx_accum=mem_acc, w_accum=w_acc)
             a = ops.CrossAttention.apply(q, kv, ca.in_proj_bias if tf else None, in_kpm, H, p, self._impl(), tf)
             a = ops.linear(a, ca.out_proj.weight, None if tf else ca.out_proj.bias, tf32=tf, round_dx=True)
             y, y_r = self._add_ln(y, a, layer.norm2, self.layer_eps, p, tf, ca.out_proj.bias)

@@ -557,10 +557,16 @@ class Linear(Function):
     def forward(ctx, x, W, b, W_r, relu, p_drop, round_out, round_dx, *extra):       # extra: an optional DxAccum
         _require_cuda(x, W)
         dx_accum = extra[0] if extra else None
+        # extra[1] = (r0, r1, DxAccum): W is the FULL parameter, W_r its rows r0:r1; the weight gradient of the slice is written
+        # into rows r0:r1 of ONE zeroed full-size buffer shared by the nodes that use disjoint row ranges of the parameter (the q
+        # and k/v rows of a cross-attention in-projection) -- no slice-backward fills / copies and no add of two full gradients
+        ctx.w_rows = extra[1] if len(extra) > 1 else None
+        if ctx.w_rows is not None:
+            ctx.w_rows[2].n_fwd += 1
         ctx.dx_accum, ctx.n_extra = dx_accum, len(extra)
         if dx_accum is not None:
             dx_accum.n_fwd += 1
-        K, N = W.shape[1], W.shape[0]
+        K, N = W_r.shape[1], W_r.shape[0]
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -571,6 +577,7 @@ class Linear(Function):
         gemm_tf32(x2, W_r, y, M, N, K, lda=K, ldb=W_r.stride(0), ldc=N, bias=b, relu=relu, p_drop=p_drop, seed=seed, off=off,
                   round_out=round_out)
         ctx.save_for_backward(x2, W_r, y if (relu or p_drop > 0) else None)
+        ctx.w_full_rows = W.shape[0]
         ctx.cfg = (relu, p_drop, b is not None, x.shape, round_dx)
         return y.view(*x.shape[:-1], N)
 
@@ -615,10 +622,23 @@ class Linear(Function):
             gemm_tf32(dy2, W_r, dx, M, K, N, lda=ldn, ldb=W_r.stride(0), ldc=K, b_mn=True, round_out=round_dx)
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1]:
-            dW = _zeros((N, K), dy.device)
+            dW_full = None
+            if ctx.w_rows is not None:
+                r0, r1, wacc = ctx.w_rows
+                first = wacc.buf is None
+                if first:
+                    wacc.buf = _zeros((ctx.w_full_rows, K), dy.device)
+                dW, dW_full = wacc.buf[r0:r1], (wacc.buf if first else None)
+                wacc.n_bwd += 1
+                if wacc.n_bwd == wacc.n_fwd:
+                    wacc.buf, wacc.n_bwd = None, 0
+            else:
+                dW = _zeros((N, K), dy.device)
             tiles = ((N + 127) // 128) * ((K + 255) // 256 if K % 256 == 0 else (K + 127) // 128)
             gemm_tf32(dy2, x2, dW, N, K, M, lda=ldn, ldb=K, ldc=K, a_mn=True, b_mn=True,
                       split_k=_split_k(tiles, (M + 31) // 32), accumulate=True)
+            if ctx.w_rows is not None:
+                dW = dW_full
         return (dx, dW, db, None, None, None, None, None) + (None,) * ctx.n_extra
 
 
@@ -718,7 +738,8 @@ FFN_FUSED = os.environ.get('PLANK_B200_FFN_FUSED', '1') == '1'        # A/B swit
 DX_ACCUM = os.environ.get('PLANK_B200_DX_ACCUM', '1') == '1'          # A/B switch for ops.DxAccum (shared input gradients)
 
 
-def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True, dx_accum=None):
+def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=False, round_dx=False, bias_grad=True, dx_accum=None,
+           w_accum=None):
     """Dense projection y = x W[rows]^T + b[rows].
     tf32=True : our tcgen05 TF32 GEMM (training path; x must be a TF32-rounded tensor).
     tf32=False: fp32-class result.  Without autograd (inference) it is the same tcgen05 kernel fed error-compensated
@@ -730,6 +751,8 @@ def linear(x, W, b, rows=None, relu=False, p_drop=0.0, tf32=False, round_out=Fal
         bv = bv.detach()                 # bias is added here, its gradient comes from the consumer kernel
     if tf32:
         W_r = tf32_weight(W)
+        if rows is not None and w_accum is not None and DX_ACCUM:
+            return Linear.apply(x, W, bv, W_r[rows], relu, p_drop, round_out, round_dx, dx_accum, (rows.start, rows.stop, w_accum))
         return Linear.apply(x, Wv, bv, W_r if rows is None else W_r[rows], relu, p_drop, round_out, round_dx, dx_accum)
     if GEMM_IMPL == 'tc' and not torch.is_grad_enabled() and p_drop == 0.0 and W.shape[1] % 4 == 0:
         return linear_x3(x, W, b, rows, relu)        # inference: our own tensor-core kernel in 3xTF32, no cuBLAS
