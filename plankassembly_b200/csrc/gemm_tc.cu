@@ -4,9 +4,10 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer  (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
 //   warp 1      MMA issuer    (tcgen05.mma.cta_group::1.kind::tf32, one elected lane) + TMEM owner
-//   warps 2..9  epilogue      (tcgen05.ld 32x32b -> bias/ReLU/Philox dropout/TF32 rounding -> 128B-swizzled smem
+//   warps 2..9  epilogue      (tcgen05.ld 32x32b -> alpha / bias / ReLU / bit-plane mask / bit-sliced dropout / column sums /
+//                              TF32 rounding, each stage a 32-wide loop of independent operations -> 128B-swizzled smem
 //                              tile -> TMA store or reduce-add); two warps per TMEM lane quarter take alternate
-//                              32-column chunks, each with its own staging tile
+//                              32-column chunks, each warp with two staging tiles
 // Three pipelines: smem full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators
 // (MMA <-> epilogue), static persistent tile schedule.
 //
