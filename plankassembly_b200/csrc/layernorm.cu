@@ -51,11 +51,12 @@ static inline int ln_max_blocks() {
   return pa_num_sms() * per_sm;
 }
 
-// Sub-block output dropout of the residual rows: 16 random bits per element, one Philox4x32-10 call per PAIR of float4
+// Sub-block output dropout of the residual rows: 16 random bits per element, one Philox4x32-7 call (the Crush-resistant round
+// count, as in the attention planes) per PAIR of float4
 // chunks of a lane (chunk i uses the low halves of the four words when i is even, the high halves when it is odd).
 // Forward and backward derive the same keep-mask from (seed, offset, row, lane, i).
 __device__ __forceinline__ uint4 ln_drop_words(uint64_t seed, uint64_t offset, int64_t row, int d4, int lane, int i) {
-  return philox4x32(seed, (uint64_t)(row * (d4 / 2 + 32) + lane + (i >> 1) * 32), offset);
+  return philox4x32<7>(seed, (uint64_t)(row * (d4 / 2 + 32) + lane + (i >> 1) * 32), offset);
 }
 __device__ __forceinline__ uint32_t ln_half(uint32_t w, int i) { return (i & 1) ? (w >> 16) : (w & 0xffffu); }
 
