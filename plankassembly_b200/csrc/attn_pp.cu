@@ -5,18 +5,21 @@
 // bursts, and QK^T / softmax / PV of a tile are one dependent chain -- the timeline (scripts/trace_attn.py) shows ~3.9 k
 // cycles per 128x128 tile against ~1.1 k issue cycles and 1 k MUFU cycles.  Here a CTA owns a PAIR of query tiles of one
 // (batch, head):
-//   * warpgroup 1+g (warps 4+4g .. 7+4g) owns query tile g: one thread = one query row = one TMEM lane, all 128 keys of a
-//     tile in registers -- no cross-group exchange, no per-tile named barrier;
-//   * the tensor pipe alternates between the tiles:  PV_A(j) QK_A(j+1) | PV_B(j) QK_B(j+1) | ...  so the MMAs of one tile
-//     run under the softmax of the other; K and V tiles are loaded ONCE for both query tiles;
-//   * O accumulates in TMEM across key tiles (tcgen05.mma accumulate) instead of a per-tile read-out into registers;
+//   * warpgroup 1+g (warps 4+4g .. 7+4g) owns query tile g: one thread = one query row = one TMEM lane, a whole row of a
+//     64-key step in registers -- no cross-group exchange, no per-tile named barrier;
+//   * K and V tiles (128 keys) are loaded ONCE for both query tiles and consumed as two 64-key steps; S is double-buffered
+//     per query tile (S_g[0] | S_g[1] = the two halves), so QK^T of step t+2 is issued right behind P V of step t and the
+//     softmax of a tile never waits for its next S; the tensor pipe alternates  PV_A QK_A | PV_B QK_B | ...  and the MMAs of
+//     one tile run under the softmax of the other;
+//   * the stationary Q tiles are copied into TMEM by their softmax warpgroups (TMEM A-operand: 32 instead of 48 cycles per
+//     128x64x8 MMA) and their shared-memory tiles are released at once for the next item's loads;
+//   * O accumulates in TMEM across key steps (tcgen05.mma accumulate) instead of a per-tile read-out into registers;
 //     it is rescaled there only when a row's running maximum grows by more than 2^8 (exact: probabilities are then taken
 //     relative to a stale maximum and may exceed 1, which fp32 / TF32 hold without loss), so the per-tile
 //     O handshake disappears;
-//   * S and P share one TMEM buffer per tile (P overwrites S; the in-order tensor pipe makes PV_g(j) read it before
-//     QK_g(j+1) overwrites it).
-// TMEM: S_A | S_B (2 x 128 columns), O_A | O_B (2 x DH), Q_A | Q_B (2 x DH: A-operands of QK^T).  Shared memory: Q_A, Q_B, two K stages, two V stages (32 KB each
-// at DH = 64) + the per-item key-bias tables.
+//   * P overwrites S in place (the in-order tensor pipe makes PV_g(t) read it before QK_g(t+2) overwrites the buffer).
+// TMEM: S_A | S_B (2 x 2 x 64 columns), O_A | O_B (2 x DH), Q_A | Q_B (2 x DH).  Shared memory: Q_A, Q_B, two K stages, two
+// V stages (32 KB each at DH = 64) + the per-item key-bias tables.
 // Used when the number of query tiles is even; attn_tc.cu keeps odd counts (a single 128-row tile: T = 128).
 //   Reference: torch nn/functional.py multi_head_attention_forward as reached from ref models.py:206,212.
 #include "common.cuh"
